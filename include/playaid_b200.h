@@ -1,0 +1,139 @@
+/*
+ * playaid_b200.h -- C ABI of the B200-native fighter action-recognition hot path.
+ *
+ * The reference (NathanBWaters/playaid_core) is pure Python and has no FFI; its boundary for
+ * this path is a set of Python call sites. Each entry point below names the reference code it
+ * replaces (paths relative to the reference root). INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions: every function returns an int status (PA_OK == 0, negative == error, never
+ * throws / exits); pointers are caller-owned DEVICE pointers unless marked "host"; every launch
+ * takes an explicit CUDA stream (cudaStream_t passed as void*); no allocation happens after
+ * pa_model_finalize() except lazily cached TMA descriptors (host memory).
+ */
+#ifndef PLAYAID_B200_H
+#define PLAYAID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_ABI_VERSION 1
+
+/* status codes */
+#define PA_OK 0
+#define PA_ERR_INVALID_ARG (-1)
+#define PA_ERR_CUDA (-2)
+#define PA_ERR_UNSUPPORTED (-3)
+#define PA_ERR_NOT_READY (-4)
+#define PA_ERR_WORKSPACE (-5)
+#define PA_ERR_MISSING_TENSOR (-6)
+
+/* per-crop status written by pa_preprocess (mirrors YoloCrop.square_crop's outcomes) */
+#define PA_CROP_OK 1        /* reference returns (True, crop)                                    */
+#define PA_CROP_INVALID 0   /* reference returns (False, None): empty window / PIL ValueError    */
+#define PA_CROP_ZERO_DIV (-2) /* reference lets ZeroDivisionError escape (square_dim == 0)       */
+#define PA_CROP_TOO_LARGE (-7) /* window wider than PA_MAX_WINDOW pixels: not computed            */
+
+/* element types / layouts */
+#define PA_DTYPE_U8 0
+#define PA_DTYPE_BF16 1
+#define PA_DTYPE_F32 2
+#define PA_DTYPE_BF16X2 3 /* bf16 hi plane followed by a bf16 lo (rounding residual) plane */
+#define PA_LAYOUT_NHWC 0
+#define PA_LAYOUT_NCHW 1
+#define PA_LAYOUT_NHWC4 2 /* 4 channels per pixel, channel 3 == 0: the conv1-ready layout */
+
+/* classifier arithmetic (pa_model_finalize) */
+#define PA_PREC_BF16 0   /* bf16 operands, fp32 accumulate: 1 tcgen05 MMA per k-step            */
+#define PA_PREC_BF16X2 1 /* activations split hi+lo bf16, weights bf16: 2 MMAs; exact to ~1e-5
+                            when the weights are bf16-representable                              */
+#define PA_PREC_BF16X3 2 /* weights split as well: 3 MMAs, for arbitrary fp32 checkpoints        */
+
+#define PA_BOX_STRIDE 8 /* int32 per crop record */
+/* crop record layout: {frame_index, cx, cy, cw, ch, reserved, reserved, reserved}; (cx,cy,cw,ch)
+ * are YoloCrop.yolo_pixels(W, H), i.e. int() truncations (playaid/fighter.py:305-314). */
+
+#define PA_MAX_WINDOW 1920 /* widest raw window (pixels) the preprocess kernel stages */
+
+typedef struct pa_ctx pa_ctx;
+typedef struct pa_model pa_model;
+
+int pa_abi_version(void);
+const char* pa_status_string(int status);
+/* last CUDA error text seen by this context (host string, valid until the next call) */
+const char* pa_last_error(pa_ctx* ctx);
+
+int pa_ctx_create(int device, pa_ctx** out);
+int pa_ctx_destroy(pa_ctx* ctx);
+
+/*
+ * Fused crop -> Pillow-BICUBIC letterbox -> OpenCV INTER_AREA -> (127-row letterbox) ->
+ * channel swap -> /255 -> (x-mean)/std -> cast. One launch for all crops.
+ * Replaces: YoloCrop.square_crop (playaid/fighter.py:323-381) incl. PIL.ImageOps.pad and
+ * imutils.resize / cv2.resize(INTER_AREA); cv2.cvtColor(BGR2RGB) + permute + .float()/255
+ * (playaid/ult_action_dataset.py:302,349-359; playaid/ai_runner.py:448,461-463); the per-frame
+ * loop of playaid/data_gen_scripts/gen_gt_action_detection.py:38-56.
+ *
+ * frames   u8 [n_frames][H][W][3], row pitch `pitch_bytes`, frame stride `frame_stride_bytes`
+ * boxes    int32 [n_crops][PA_BOX_STRIDE]
+ * out      [n_crops][out][out][3] (NHWC) or [n_crops][3][out][out] (NCHW) of out_dtype.
+ *          PA_DTYPE_U8 ignores mean/std and stores the resampled bytes (square_crop's result).
+ *          Crops whose status != PA_CROP_OK are written as zeros.
+ * status   int32 [n_crops] or NULL
+ */
+int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, int64_t pitch_bytes,
+                  int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,
+                  int swap_rb, const float* mean3_host, const float* std3_host, void* out, int out_dtype,
+                  int out_layout, int32_t* status, void* stream);
+
+/*
+ * Classifier. Replaces CNNActionDetector / SpatialStreamCNN forward
+ * (playaid/models/cnn_action_detector.py:13-43,86-92) and the argmax / exp head of
+ * AIRunner.action_recognition (playaid/ai_runner.py:472-477).
+ */
+int pa_model_create(pa_ctx* ctx, int n_actions, int seq_len, pa_model** out);
+int pa_model_destroy(pa_model* m);
+/* Hand over one state_dict entry (host fp32, contiguous, PyTorch layout) under the reference's
+ * key, e.g. "model.cnn2d.layer1.0.conv1.weight", "model.cnn1d.0.bias", "model.classifier.2.weight".
+ * Keys ending in "num_batches_tracked" are ignored. */
+int pa_model_set_tensor(pa_model* m, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* Fold eval-mode BatchNorm into fp32 scale/shift, pack the weights for the kernels, upload. */
+int pa_model_finalize(pa_model* m, int precision);
+int pa_model_precision(const pa_model* m);
+/* Workspace needed to push `n_crops` crops through the CNN (activations of every layer). */
+int pa_model_workspace_bytes(const pa_model* m, int n_crops, size_t* bytes);
+
+/*
+ * ResNet-18 features, once per crop. crops: bf16 NHWC4 [n_crops][128][128][4] (channel 3 == 0)
+ * as written by pa_preprocess(out_dtype=PA_DTYPE_BF16, out_layout=PA_LAYOUT_NHWC) with the
+ * 4-channel pitch this library uses internally -- see pa_crop_elems(); in PA_PREC_BF16X2/X3 the
+ * lo plane follows the hi plane. feat: fp32 [n_crops][1000].
+ */
+int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* Elements (of out_dtype) per crop in the internal conv-ready layout. */
+size_t pa_crop_elems(int out_size);
+
+/*
+ * Temporal head over windows of cached features: Conv1d(1000->512,k=seq)+ReLU, Linear+ReLU,
+ * Linear, log_softmax, argmax (first maximum of the log-probs), exp(log-prob of the label).
+ * feat      fp32 [n_feat][1000]
+ * win_idx   int32 [n_win][seq_len] rows of feat (action_sample_from_frame_middle_out,
+ *           playaid/dataset_utils.py:109-138, already offset into feat)
+ * logp      fp32 [n_win][n_actions]; label int32 [n_win]; conf fp32 [n_win] (probability;
+ *           AIRunner multiplies by 100.0 on the host)
+ */
+int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, int n_win, float* logp,
+            int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t pa_launch_count(pa_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAYAID_B200_H */

@@ -1,0 +1,280 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (sm_100a).
+//
+//   D[M, Cout] = A[M, K] * W[Cout, K]^T,  M = output pixels of all crops (NHWC), K = taps * Cin
+//
+// * A is never materialised: for every filter tap the TMA engine loads a 4-D box
+//   [64 channels, Wt, Ht, Nt] (Wt*Ht*Nt = 128 output pixels) straight from the NHWC activation;
+//   out-of-bounds coordinates are zero-filled by the TMA unit, which implements the conv padding.
+//   Stride-2 layers use four parity views of the input (one tensor map per (y&1, x&1)).
+// * W tiles [BLOCK_N, 64] come from a K-major packed weight matrix through a 2-D tensor map.
+// * Both operands land in shared memory in the canonical K-major SWIZZLE_128B layout and are
+//   consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) with the fp32 accumulator in
+//   TMEM (double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+//   (TMEM -> registers -> folded-BN scale/shift (+ residual) (+ ReLU) -> bf16 / fp32 global).
+// * Split precision (PA_PREC_BF16X2 / X3): activations (and optionally weights) carry a bf16
+//   "lo" plane with the rounding residual; the extra products are accumulated into the same
+//   TMEM tile, reusing the staged weight tile.
+//
+// Replaces the cuDNN/oneDNN calls behind torchvision.resnet18 + nn.Conv1d/nn.Linear in
+// playaid/models/cnn_action_detector.py:13-43.
+#include "pa_internal.cuh"
+#include "ptx.cuh"
+
+namespace pa {
+
+constexpr int CG_THREADS = 192;
+constexpr int CG_BLOCK_M = 128;
+constexpr int CG_BLOCK_K = 64;
+constexpr int CG_A_BYTES = CG_BLOCK_M * CG_BLOCK_K * 2;  // 16 KB
+
+size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages) {
+    size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
+    return 1024 /*alignment slack*/ + stage * num_stages + 256 /*barriers*/;
+}
+int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
+    size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
+    int s = (int)((227 * 1024 - 1024 - 256) / stage);
+    if (s > 8) s = 8;
+    return s;
+}
+
+template <int BLOCK_N, int NA, int NB>
+__global__ void __launch_bounds__(CG_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int B_BYTES = BLOCK_N * CG_BLOCK_K * 2;
+    constexpr int STAGE_BYTES = NA * CG_A_BYTES + NB * B_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    const int S = args.num_stages;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* tfull = bars + 2 * S;
+    uint64_t* tempty = bars + 2 * S + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = args.taps_h * args.taps_w;
+    const int num_kb = taps * args.kb_per_tap;
+    const int total_tiles = args.m_tiles * args.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int pl = 0; pl < NA; pl++)
+            for (int q = 0; q < (args.stride == 2 ? 4 : 1); q++) tma_prefetch_desc(&maps.a[pl][q]);
+        for (int pl = 0; pl < NB; pl++) tma_prefetch_desc(&maps.b[pl]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            const int pix_per_img = args.ho * args.wo;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
+                const int m0 = mt * CG_BLOCK_M;
+                const int n0 = m0 / pix_per_img;
+                const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
+                for (int tap = 0; tap < taps; tap++) {
+                    const int ky = tap / args.taps_w, kx = tap - ky * args.taps_w;
+                    int cx, cy, q = 0;
+                    if (args.stride == 1) {
+                        cx = kx - args.pad; cy = oy0 + ky - args.pad;
+                    } else {
+                        const int dx = kx - args.pad, dy = ky - args.pad;
+                        const int px = dx & 1, py = dy & 1;
+                        q = py * 2 + px;
+                        cx = (dx - px) / 2; cy = oy0 + (dy - py) / 2;
+                    }
+                    for (int kc = 0; kc < args.kb_per_tap; kc++) {
+                        mbar_wait(&empty[st], ph ^ 1);
+                        uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
+                        uint8_t* sb = sa + NA * CG_A_BYTES;
+                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+#pragma unroll
+                        for (int pl = 0; pl < NA; pl++)
+                            tma_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
+#pragma unroll
+                        for (int pl = 0; pl < NB; pl++)
+                            tma_load_2d(sb + pl * B_BYTES, &maps.b[pl], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                        if (++st == S) { st = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(CG_BLOCK_M, BLOCK_N);
+            int st = 0; uint32_t ph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+                const int acc = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+                    const uint32_t sb = sa + NA * CG_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < CG_BLOCK_K / 16; k++) {
+                        const uint64_t da = umma_desc_sw128(sa + k * 32);
+                        const uint64_t db = umma_desc_sw128(sb + k * 32);
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                        if (NA == 2) umma_bf16(d_tmem, umma_desc_sw128(sa + CG_A_BYTES + k * 32), db, idesc, 1);
+                        if (NB == 2) umma_bf16(d_tmem, da, umma_desc_sw128(sb + B_BYTES + k * 32), idesc, 1);
+                    }
+                    umma_commit(&empty[st]);
+                    if (++st == S) { st = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], acc_ph);
+            tc_fence_after();
+            const int64_t row = (int64_t)mt * CG_BLOCK_M + r;
+            const bool row_ok = row < args.m_total;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                float v[16];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after per-row predication
+                tmem_ld16(t_addr + c0, v);
+                const int n = nt * BLOCK_N + c0;
+                if (n >= args.cout) continue;  // warp-uniform
+                if (args.scale) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] = v[i] * __ldg(args.scale + n + i);
+                }
+                if (args.shift) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] = v[i] + __ldg(args.shift + n + i);
+                }
+                if (!row_ok) continue;
+                const int64_t o = row * args.cout + n;
+                const bool full16 = (n + 16 <= args.cout);
+                if (args.res_hi) {
+                    if (full16) {
+                        const uint4* rp = (const uint4*)(args.res_hi + o);
+                        uint4 a = __ldg(rp), b = __ldg(rp + 1);
+                        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            v[2 * i] += __uint_as_float(w[i] << 16);
+                            v[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+                        }
+                        if (args.res_lo) {
+                            const uint4* lp = (const uint4*)(args.res_lo + o);
+                            uint4 c = __ldg(lp), d = __ldg(lp + 1);
+                            const uint32_t x[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                v[2 * i] += __uint_as_float(x[i] << 16);
+                                v[2 * i + 1] += __uint_as_float(x[i] & 0xFFFF0000u);
+                            }
+                        }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
+                            v[i] += __bfloat162float(args.res_hi[o + i]);
+                            if (args.res_lo) v[i] += __bfloat162float(args.res_lo[o + i]);
+                        }
+                    }
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (args.out_f32) {
+                    if (full16 && ((o & 3) == 0)) {
+                        float4* op = (float4*)(args.out_f32 + o);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) args.out_f32[o + i] = v[i];
+                    }
+                }
+                if (args.out_hi) {
+                    if (full16 && ((o & 7) == 0)) {
+                        uint32_t h[8], l[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const bf16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+                            h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            if (args.out_lo) l[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+                        }
+                        uint4* op = (uint4*)(args.out_hi + o);
+                        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                        if (args.out_lo) {
+                            uint4* lp = (uint4*)(args.out_lo + o);
+                            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                        }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
+                            const bf16 h0 = __float2bfloat16_rn(v[i]);
+                            args.out_hi[o + i] = h0;
+                            if (args.out_lo) args.out_lo[o + i] = __float2bfloat16_rn(v[i] - __bfloat162float(h0));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BLOCK_N, int NA, int NB>
+static int launch_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cudaStream_t stream) {
+    auto kern = conv_gemm_kernel<BLOCK_N, NA, NB>;
+    const size_t smem = conv_gemm_smem_bytes(BLOCK_N, NA, NB, args.num_stages);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return PA_ERR_CUDA;
+        attr_set = true;
+    }
+    int grid = args.m_tiles * args.n_tiles;
+    if (grid > num_sms) grid = num_sms;
+    kern<<<grid, CG_THREADS, smem, stream>>>(maps, args);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
+int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms, cudaStream_t stream) {
+#define PA_CG_CASE(BN, A, B) \
+    if (block_n == BN && n_a == A && n_b == B) return launch_t<BN, A, B>(maps, args, num_sms, stream);
+    PA_CG_CASE(64, 1, 1) PA_CG_CASE(128, 1, 1) PA_CG_CASE(256, 1, 1)
+    PA_CG_CASE(64, 2, 1) PA_CG_CASE(128, 2, 1) PA_CG_CASE(256, 2, 1)
+    PA_CG_CASE(64, 2, 2) PA_CG_CASE(128, 2, 2) PA_CG_CASE(256, 2, 2)
+#undef PA_CG_CASE
+    return PA_ERR_UNSUPPORTED;
+}
+
+}  // namespace pa

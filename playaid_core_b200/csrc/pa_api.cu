@@ -1,0 +1,630 @@
+// C-ABI of the B200-native fighter action-recognition path (see include/playaid_b200.h).
+// Host-side orchestration only: weight packing, BatchNorm folding, TMA descriptor construction,
+// workspace carving and kernel sequencing. No PyTorch types cross this boundary.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pa_internal.cuh"
+
+using namespace pa;
+
+// ------------------------------------------------------------------------------------------------
+struct pa_ctx {
+    int device = 0;
+    int num_sms = 148;
+    int64_t launches = 0;
+    std::string last_error;
+    decltype(&cuTensorMapEncodeTiled) encode_tiled = nullptr;
+};
+
+static int cuda_fail(pa_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return PA_ERR_CUDA;
+}
+#define PA_CUDA(ctx, expr)                                            \
+    do {                                                              \
+        cudaError_t _e = (expr);                                      \
+        if (_e != cudaSuccess) return cuda_fail((ctx), _e, #expr);    \
+    } while (0)
+
+extern "C" int pa_abi_version(void) { return PA_ABI_VERSION; }
+
+extern "C" const char* pa_status_string(int s) {
+    switch (s) {
+        case PA_OK: return "ok";
+        case PA_ERR_INVALID_ARG: return "invalid argument";
+        case PA_ERR_CUDA: return "CUDA error (see pa_last_error)";
+        case PA_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PA_ERR_NOT_READY: return "model not finalized";
+        case PA_ERR_WORKSPACE: return "workspace too small";
+        case PA_ERR_MISSING_TENSOR: return "state_dict tensor missing or wrong shape";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* pa_last_error(pa_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+extern "C" int pa_ctx_create(int device, pa_ctx** out) {
+    if (!out) return PA_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PA_ERR_CUDA;
+    pa_ctx* ctx = new pa_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return PA_ERR_CUDA;
+    }
+    if (prop.major != 10) {  // sm_100a only: tcgen05 / TMEM
+        delete ctx;
+        return PA_ERR_UNSUPPORTED;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        delete ctx;
+        return PA_ERR_CUDA;
+    }
+    ctx->encode_tiled = (decltype(&cuTensorMapEncodeTiled))fn;
+    *out = ctx;
+    return PA_OK;
+}
+
+extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
+    delete ctx;
+    return PA_OK;
+}
+
+extern "C" int64_t pa_launch_count(pa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ preprocess
+extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, int64_t pitch_bytes,
+                             int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,
+                             int swap_rb, const float* mean3, const float* std3, void* out, int out_dtype,
+                             int out_layout, int32_t* status, void* stream) {
+    if (!ctx || !frames || !boxes || !out || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
+    if (out_size <= 0 || out_size > 1024 || padding < 0) return PA_ERR_INVALID_ARG;
+    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_BF16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4)
+        return PA_ERR_INVALID_ARG;
+    if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
+    if (n_crops == 0) return PA_OK;
+    PPParams p;
+    p.frames = frames;
+    p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
+    p.n_frames = n_frames; p.H = H; p.W = W;
+    p.pitch = pitch_bytes; p.fstride = frame_stride_bytes;
+    p.boxes = boxes; p.n_crops = n_crops; p.out = out_size; p.padding = padding; p.swap_rb = swap_rb ? 1 : 0;
+    for (int c = 0; c < 3; c++) {
+        p.mean[c] = mean3 ? mean3[c] : 0.f;
+        p.stdv[c] = std3 ? std3[c] : 1.f;
+    }
+    p.outp = out; p.out_dtype = out_dtype; p.out_layout = out_layout;
+    const int ch = (out_layout == PA_LAYOUT_NHWC4) ? 4 : 3;
+    p.plane_elems = (int64_t)n_crops * out_size * out_size * ch;
+    p.status = status;
+    p.smem_bytes = 100 * 1024;
+    int rc = launch_preprocess(p, (cudaStream_t)stream);
+    if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
+    ctx->launches += 1;
+    return PA_OK;
+}
+
+extern "C" size_t pa_crop_elems(int out_size) { return (size_t)out_size * out_size * 4; }
+
+// ------------------------------------------------------------------------------------------------ model
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct ConvLayer {
+    std::string w_key, bn_key;  // bn_key empty -> bias_key used
+    std::string bias_key;
+    int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+    int hin = 0;                 // input spatial size (square)
+    bool relu = false;
+    // device
+    bf16 *w_hi = nullptr, *w_lo = nullptr;
+    float *scale = nullptr, *shift = nullptr;
+    int k_total = 0;
+    int block_n = 64;
+};
+
+struct PlanOp {
+    int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool
+    Conv1Args c1;
+    ConvMaps maps;
+    ConvArgs args;
+    int block_n, n_a, n_b;
+    // pools
+    const bf16 *pin_hi, *pin_lo;
+    bf16 *pout_hi, *pout_lo;
+    int pn, ph, pw, pc;
+};
+
+struct pa_model {
+    pa_ctx* ctx = nullptr;
+    int n_actions = 0, seq = 0;
+    int precision = -1;
+    bool ready = false;
+    std::map<std::string, HostTensor> tensors;
+    ConvLayer stem;
+    std::vector<ConvLayer> convs;  // resnet body in execution order (incl. downsample)
+    ConvLayer fc, proj;
+    float *b1d = nullptr, *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;
+    bf16 *stem_w_hi = nullptr, *stem_w_lo = nullptr;
+    std::vector<void*> dev_allocs;
+    // cached forward plan
+    std::vector<PlanOp> plan;
+    const void* plan_crops = nullptr;
+    void* plan_ws = nullptr;
+    float* plan_feat = nullptr;
+    int plan_n = -1;
+    // cached head plan
+    PlanOp head_gemm;
+    const float* hplan_feat = nullptr;
+    void* hplan_ws = nullptr;
+    int hplan_n = -1;
+};
+
+static inline uint16_t f2bf(float f) {  // round-to-nearest-even, like __float2bfloat16_rn
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+extern "C" int pa_model_create(pa_ctx* ctx, int n_actions, int seq_len, pa_model** out) {
+    if (!ctx || !out || n_actions <= 0 || n_actions > 128 || seq_len <= 0 || seq_len > 15 || (seq_len % 2) == 0) return PA_ERR_INVALID_ARG;
+    pa_model* m = new pa_model();
+    m->ctx = ctx; m->n_actions = n_actions; m->seq = seq_len;
+    *out = m;
+    return PA_OK;
+}
+
+extern "C" int pa_model_destroy(pa_model* m) {
+    if (!m) return PA_OK;
+    for (void* p : m->dev_allocs) cudaFree(p);
+    delete m;
+    return PA_OK;
+}
+
+extern "C" int pa_model_set_tensor(pa_model* m, const char* name, const float* host, const int64_t* shape, int ndim) {
+    if (!m || !name || !host || ndim < 0 || ndim > 8) return PA_ERR_INVALID_ARG;
+    std::string key(name);
+    if (key.rfind("model.", 0) == 0) key = key.substr(6);
+    if (key.size() >= 19 && key.compare(key.size() - 19, 19, "num_batches_tracked") == 0) return PA_OK;
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) { t.shape.push_back(shape[i]); n *= shape[i]; }
+    t.data.assign(host, host + n);
+    m->tensors[key] = std::move(t);
+    m->ready = false;
+    return PA_OK;
+}
+
+static const HostTensor* get_tensor(pa_model* m, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = m->tensors.find(key);
+    if (it == m->tensors.end()) { m->ctx->last_error = "missing tensor " + key; return nullptr; }
+    if (it->second.shape != std::vector<int64_t>(shape)) { m->ctx->last_error = "bad shape for " + key; return nullptr; }
+    return &it->second;
+}
+
+template <typename T>
+static int upload(pa_model* m, const std::vector<T>& host, T** dev) {
+    void* p = nullptr;
+    PA_CUDA(m->ctx, cudaMalloc(&p, host.size() * sizeof(T) + 16));
+    m->dev_allocs.push_back(p);
+    PA_CUDA(m->ctx, cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (T*)p;
+    return PA_OK;
+}
+
+static void split_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+    hi.resize(w.size()); lo.resize(w.size());
+    for (size_t i = 0; i < w.size(); i++) {
+        hi[i] = f2bf(w[i]);
+        lo[i] = f2bf(w[i] - bf2f(hi[i]));
+    }
+}
+
+// pack [cout][cin][k][k] -> [cout][tap][cin], fold BN (or bias) into scale/shift, upload
+static int prepare_conv(pa_model* m, ConvLayer& L) {
+    const HostTensor* w = get_tensor(m, L.w_key, {L.cout, L.cin, L.k, L.k});
+    if (!w) return PA_ERR_MISSING_TENSOR;
+    const int taps = L.k * L.k;
+    L.k_total = taps * L.cin;
+    std::vector<float> packed((size_t)L.cout * L.k_total);
+    for (int o = 0; o < L.cout; o++)
+        for (int c = 0; c < L.cin; c++)
+            for (int t = 0; t < taps; t++)
+                packed[((size_t)o * taps + t) * L.cin + c] = w->data[((size_t)o * L.cin + c) * taps + t];
+    std::vector<uint16_t> hi, lo;
+    split_weights(packed, hi, lo);
+    int rc = upload(m, hi, (uint16_t**)&L.w_hi);
+    if (rc != PA_OK) return rc;
+    if (m->precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
+    std::vector<float> scale(L.cout, 1.f), shift(L.cout, 0.f);
+    if (!L.bn_key.empty()) {
+        const HostTensor *g = get_tensor(m, L.bn_key + ".weight", {L.cout}), *b = get_tensor(m, L.bn_key + ".bias", {L.cout}),
+                         *mu = get_tensor(m, L.bn_key + ".running_mean", {L.cout}), *var = get_tensor(m, L.bn_key + ".running_var", {L.cout});
+        if (!g || !b || !mu || !var) return PA_ERR_MISSING_TENSOR;
+        for (int o = 0; o < L.cout; o++) {
+            const double s = (double)g->data[o] / std::sqrt((double)var->data[o] + 1e-5);
+            scale[o] = (float)s;
+            shift[o] = (float)((double)b->data[o] - (double)mu->data[o] * s);
+        }
+    } else if (!L.bias_key.empty()) {
+        const HostTensor* b = get_tensor(m, L.bias_key, {L.cout});
+        if (!b) return PA_ERR_MISSING_TENSOR;
+        for (int o = 0; o < L.cout; o++) shift[o] = b->data[o];
+    }
+    rc = upload(m, scale, &L.scale); if (rc != PA_OK) return rc;
+    rc = upload(m, shift, &L.shift); if (rc != PA_OK) return rc;
+    return PA_OK;
+}
+
+static ConvLayer make_conv(const std::string& w, const std::string& bn, int cin, int cout, int k, int stride, int pad, int hin, bool relu) {
+    ConvLayer L;
+    L.w_key = w; L.bn_key = bn; L.cin = cin; L.cout = cout; L.k = k; L.stride = stride; L.pad = pad; L.hin = hin; L.relu = relu;
+    L.block_n = cout >= 256 ? 256 : cout;
+    return L;
+}
+
+extern "C" int pa_model_finalize(pa_model* m, int precision) {
+    if (!m) return PA_ERR_INVALID_ARG;
+    if (precision < PA_PREC_BF16 || precision > PA_PREC_BF16X3) return PA_ERR_INVALID_ARG;
+    pa_ctx* ctx = m->ctx;
+    PA_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (void* p : m->dev_allocs) cudaFree(p);
+    m->dev_allocs.clear();
+    m->convs.clear();
+    m->plan_n = -1; m->hplan_n = -1;
+    m->precision = precision;
+    const std::string P = "cnn2d.";
+    int rc;
+    // ---- stem: [64][3][7][7] -> [64][256] with k = ky*32 + (kx+1)*4 + c
+    {
+        const HostTensor* w = get_tensor(m, P + "conv1.weight", {64, 3, 7, 7});
+        if (!w) return PA_ERR_MISSING_TENSOR;
+        std::vector<float> packed((size_t)64 * 256, 0.f);
+        for (int o = 0; o < 64; o++)
+            for (int c = 0; c < 3; c++)
+                for (int ky = 0; ky < 7; ky++)
+                    for (int kx = 0; kx < 7; kx++)
+                        packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w->data[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
+        std::vector<uint16_t> hi, lo;
+        split_weights(packed, hi, lo);
+        rc = upload(m, hi, (uint16_t**)&m->stem_w_hi); if (rc != PA_OK) return rc;
+        m->stem_w_lo = nullptr;
+        if (precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&m->stem_w_lo); if (rc != PA_OK) return rc; }
+        m->stem = make_conv("", P + "bn1", 3, 64, 7, 2, 3, 128, true);
+        ConvLayer& L = m->stem;
+        const HostTensor *g = get_tensor(m, L.bn_key + ".weight", {64}), *b = get_tensor(m, L.bn_key + ".bias", {64}),
+                         *mu = get_tensor(m, L.bn_key + ".running_mean", {64}), *var = get_tensor(m, L.bn_key + ".running_var", {64});
+        if (!g || !b || !mu || !var) return PA_ERR_MISSING_TENSOR;
+        std::vector<float> scale(64), shift(64);
+        for (int o = 0; o < 64; o++) {
+            const double s = (double)g->data[o] / std::sqrt((double)var->data[o] + 1e-5);
+            scale[o] = (float)s;
+            shift[o] = (float)((double)b->data[o] - (double)mu->data[o] * s);
+        }
+        rc = upload(m, scale, &L.scale); if (rc != PA_OK) return rc;
+        rc = upload(m, shift, &L.shift); if (rc != PA_OK) return rc;
+    }
+    // ---- residual stages (execution order per block: conv1, [downsample], conv2)
+    const int chans[4] = {64, 128, 256, 512};
+    int hin = 32, cin = 64;
+    for (int s = 0; s < 4; s++) {
+        const int cout = chans[s];
+        for (int b = 0; b < 2; b++) {
+            const std::string B = P + "layer" + std::to_string(s + 1) + "." + std::to_string(b) + ".";
+            const int stride = (s > 0 && b == 0) ? 2 : 1;
+            m->convs.push_back(make_conv(B + "conv1.weight", B + "bn1", cin, cout, 3, stride, 1, hin, true));
+            if (stride == 2) m->convs.push_back(make_conv(B + "downsample.0.weight", B + "downsample.1", cin, cout, 1, 2, 0, hin, false));
+            m->convs.push_back(make_conv(B + "conv2.weight", B + "bn2", cout, cout, 3, 1, 1, hin / stride, true));
+            hin /= stride;
+            cin = cout;
+        }
+    }
+    for (ConvLayer& L : m->convs) { rc = prepare_conv(m, L); if (rc != PA_OK) return rc; }
+    // ---- fc as a 1x1 "conv" over pooled features
+    m->fc = make_conv(P + "fc.weight", "", 512, 1000, 1, 1, 0, 1, false);
+    m->fc.bias_key = P + "fc.bias";
+    {
+        // fc.weight is [1000][512]: view as [1000][512][1][1]
+        auto it = m->tensors.find(m->fc.w_key);
+        if (it == m->tensors.end()) { ctx->last_error = "missing tensor " + m->fc.w_key; return PA_ERR_MISSING_TENSOR; }
+        if (it->second.shape.size() == 2) { it->second.shape.push_back(1); it->second.shape.push_back(1); }
+    }
+    rc = prepare_conv(m, m->fc); if (rc != PA_OK) return rc;
+    // ---- temporal Conv1d as per-frame projections: rows n = t*512 + o, K = 1000
+    {
+        const int S = m->seq;
+        const HostTensor* w = get_tensor(m, "cnn1d.0.weight", {512, 1000, S});
+        const HostTensor* b = get_tensor(m, "cnn1d.0.bias", {512});
+        if (!w || !b) return PA_ERR_MISSING_TENSOR;
+        std::vector<float> packed((size_t)S * 512 * 1000);
+        for (int o = 0; o < 512; o++)
+            for (int i = 0; i < 1000; i++)
+                for (int t = 0; t < S; t++) packed[((size_t)t * 512 + o) * 1000 + i] = w->data[((size_t)o * 1000 + i) * S + t];
+        std::vector<uint16_t> hi, lo;
+        split_weights(packed, hi, lo);
+        ConvLayer& L = m->proj;
+        L = make_conv("", "", 1000, S * 512, 1, 1, 0, 1, false);
+        L.k_total = 1000;
+        rc = upload(m, hi, (uint16_t**)&L.w_hi); if (rc != PA_OK) return rc;
+        if (precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
+        rc = upload(m, b->data, &m->b1d); if (rc != PA_OK) return rc;
+    }
+    // ---- classifier MLP (fp32 SIMT in the head kernel), weights transposed for coalesced reads
+    {
+        const int A = m->n_actions;
+        const HostTensor *w1 = get_tensor(m, "classifier.0.weight", {128, 512}), *b1 = get_tensor(m, "classifier.0.bias", {128}),
+                         *w2 = get_tensor(m, "classifier.2.weight", {A, 128}), *b2 = get_tensor(m, "classifier.2.bias", {A});
+        if (!w1 || !b1 || !w2 || !b2) return PA_ERR_MISSING_TENSOR;
+        std::vector<float> w1t((size_t)512 * 128), w2t((size_t)128 * A);
+        for (int o = 0; o < 128; o++) for (int i = 0; i < 512; i++) w1t[(size_t)i * 128 + o] = w1->data[(size_t)o * 512 + i];
+        for (int o = 0; o < A; o++) for (int i = 0; i < 128; i++) w2t[(size_t)i * A + o] = w2->data[(size_t)o * 128 + i];
+        rc = upload(m, w1t, &m->w1t); if (rc != PA_OK) return rc;
+        rc = upload(m, b1->data, &m->b1); if (rc != PA_OK) return rc;
+        rc = upload(m, w2t, &m->w2t); if (rc != PA_OK) return rc;
+        rc = upload(m, b2->data, &m->b2); if (rc != PA_OK) return rc;
+    }
+    m->ready = true;
+    return PA_OK;
+}
+
+extern "C" int pa_model_precision(const pa_model* m) { return m ? m->precision : -1; }
+
+// activation arena: one big buffer (stem output) + four small ones, per plane
+static const size_t kBigElems = (size_t)64 * 64 * 64;    // per crop
+static const size_t kSmallElems = (size_t)32 * 32 * 64;  // per crop
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static size_t features_ws_bytes(const pa_model* m, int n) {
+    const int planes = (m->precision == PA_PREC_BF16) ? 1 : 2;
+    size_t per_plane = align256(kBigElems * n * 2) + 4 * align256(kSmallElems * n * 2) + align256((size_t)n * 512 * 2);
+    return per_plane * planes + 1024;
+}
+static size_t head_ws_bytes(const pa_model* m, int n_feat) {
+    return 2 * align256((size_t)n_feat * 1000 * 2) + align256((size_t)n_feat * m->seq * 512 * 4) + 1024;
+}
+
+extern "C" int pa_model_workspace_bytes(const pa_model* m, int n_crops, size_t* bytes) {
+    if (!m || !bytes || n_crops <= 0) return PA_ERR_INVALID_ARG;
+    if (m->precision < 0) return PA_ERR_NOT_READY;
+    size_t a = features_ws_bytes(m, n_crops), b = head_ws_bytes(m, n_crops);
+    *bytes = a > b ? a : b;
+    return PA_OK;
+}
+
+// ---- TMA descriptors
+static int make_map_a(pa_ctx* ctx, CUtensorMap* map, const bf16* base, int C, int W, int H, int N, int parity_stride,
+                      int py, int px, int wt, int ht, int nt) {
+    // parity_stride == 1: plain NHWC view. == 2: every other row / column starting at (py, px).
+    const int s = parity_stride;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(W / s), (cuuint64_t)(H / s), (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)s * C * 2, (cuuint64_t)s * W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)nt};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const bf16* p = base + ((size_t)py * W + px) * C;
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->last_error = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+static int make_map_b(pa_ctx* ctx, CUtensorMap* map, const bf16* base, int k_total, int cout, int block_n) {
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)cout};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->last_error = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+
+struct Act {  // an activation tensor: hi plane (+ lo plane)
+    bf16* hi = nullptr;
+    bf16* lo = nullptr;
+};
+
+// Build the launch record of one conv/linear layer. `hin` = input spatial size, N images.
+static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, const Act* res, const Act* out, float* out_f32, PlanOp& op) {
+    pa_ctx* ctx = m->ctx;
+    memset(&op.maps, 0, sizeof(op.maps));
+    op.kind = 2;
+    const int n_a = in.lo ? 2 : 1, n_b = L.w_lo ? 2 : 1;
+    const int hout = L.hin / L.stride;
+    int wt, ht, nt;
+    if (hout >= 32) { wt = hout; ht = 128 / hout; nt = 1; }
+    else if (hout == 16) { wt = 16; ht = 8; nt = 1; }
+    else if (hout == 8) { wt = 8; ht = 8; nt = 2; }
+    else if (hout == 4) { wt = 4; ht = 4; nt = 8; }
+    else if (hout == 1) { wt = 1; ht = 1; nt = 128; }
+    else return PA_ERR_UNSUPPORTED;
+    for (int pl = 0; pl < n_a; pl++) {
+        const bf16* base = pl == 0 ? in.hi : in.lo;
+        if (L.stride == 1) {
+            int rc = make_map_a(ctx, &op.maps.a[pl][0], base, L.cin, L.hin, L.hin, N, 1, 0, 0, wt, ht, nt);
+            if (rc != PA_OK) return rc;
+        } else {
+            for (int q = 0; q < 4; q++) {
+                int rc = make_map_a(ctx, &op.maps.a[pl][q], base, L.cin, L.hin, L.hin, N, 2, q >> 1, q & 1, wt, ht, nt);
+                if (rc != PA_OK) return rc;
+            }
+        }
+    }
+    int rc = make_map_b(ctx, &op.maps.b[0], L.w_hi, L.k_total, L.cout, L.block_n);
+    if (rc != PA_OK) return rc;
+    if (n_b == 2) { rc = make_map_b(ctx, &op.maps.b[1], L.w_lo, L.k_total, L.cout, L.block_n); if (rc != PA_OK) return rc; }
+    ConvArgs& a = op.args;
+    memset(&a, 0, sizeof(a));
+    a.m_total = N * hout * hout;
+    a.m_tiles = (a.m_total + 127) / 128;
+    a.n_tiles = (L.cout + L.block_n - 1) / L.block_n;
+    a.cout = L.cout;
+    a.taps_h = L.k; a.taps_w = L.k; a.stride = L.stride; a.pad = L.pad;
+    a.kb_per_tap = (L.cin + 63) / 64;
+    a.k_per_tap = L.cin;
+    a.ho = hout; a.wo = hout;
+    op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
+    a.num_stages = conv_gemm_pick_stages(L.block_n, n_a, n_b);
+    if (a.num_stages < 2) return PA_ERR_UNSUPPORTED;
+    a.scale = L.scale; a.shift = L.shift;
+    a.res_hi = res ? res->hi : nullptr;
+    a.res_lo = res ? res->lo : nullptr;
+    a.relu = L.relu ? 1 : 0;
+    a.out_hi = out ? out->hi : nullptr;
+    a.out_lo = out ? out->lo : nullptr;
+    a.out_f32 = out_f32;
+    return PA_OK;
+}
+
+static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat, void* ws, size_t ws_bytes) {
+    if (features_ws_bytes(m, n) > ws_bytes) return PA_ERR_WORKSPACE;
+    const bool split = m->precision != PA_PREC_BF16;
+    uint8_t* p = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    auto carve = [&](size_t elems) {
+        Act a;
+        a.hi = (bf16*)p; p += align256(elems * 2);
+        if (split) { a.lo = (bf16*)p; p += align256(elems * 2); }
+        return a;
+    };
+    Act big = carve(kBigElems * n);
+    Act sm[4];
+    for (int i = 0; i < 4; i++) sm[i] = carve(kSmallElems * n);
+    Act pooled = carve((size_t)n * 512);
+    m->plan.clear();
+    // stem
+    {
+        PlanOp op; memset(&op, 0, sizeof(op));
+        op.kind = 0;
+        op.c1.in_hi = (const bf16*)crops;
+        op.c1.in_lo = split ? (const bf16*)crops + (size_t)n * 128 * 128 * 4 : nullptr;
+        op.c1.w_hi = m->stem_w_hi; op.c1.w_lo = m->stem_w_lo;
+        op.c1.scale = m->stem.scale; op.c1.shift = m->stem.shift;
+        op.c1.out_hi = big.hi; op.c1.out_lo = big.lo;
+        op.c1.n_crops = n;
+        m->plan.push_back(op);
+    }
+    {
+        PlanOp op; memset(&op, 0, sizeof(op));
+        op.kind = 1;
+        op.pin_hi = big.hi; op.pin_lo = big.lo; op.pout_hi = sm[0].hi; op.pout_lo = sm[0].lo;
+        op.pn = n; op.ph = 64; op.pw = 64; op.pc = 64;
+        m->plan.push_back(op);
+    }
+    int x = 0;  // index of the buffer holding the block input
+    size_t ci = 0;
+    for (int s = 0; s < 4; s++) {
+        for (int b = 0; b < 2; b++) {
+            const bool down = (s > 0 && b == 0);
+            const int t = (x + 1) & 3, r = (x + 2) & 3, y = (x + 3) & 3;
+            PlanOp op;
+            int rc = plan_conv(m, m->convs[ci++], sm[x], n, nullptr, &sm[t], nullptr, op);
+            if (rc != PA_OK) return rc;
+            m->plan.push_back(op);
+            const Act* res = &sm[x];
+            if (down) {
+                rc = plan_conv(m, m->convs[ci++], sm[x], n, nullptr, &sm[r], nullptr, op);
+                if (rc != PA_OK) return rc;
+                m->plan.push_back(op);
+                res = &sm[r];
+            }
+            rc = plan_conv(m, m->convs[ci++], sm[t], n, res, &sm[y], nullptr, op);
+            if (rc != PA_OK) return rc;
+            m->plan.push_back(op);
+            x = y;
+        }
+    }
+    {
+        PlanOp op; memset(&op, 0, sizeof(op));
+        op.kind = 3;
+        op.pin_hi = sm[x].hi; op.pin_lo = sm[x].lo; op.pout_hi = pooled.hi; op.pout_lo = pooled.lo;
+        op.pn = n; op.ph = 16; op.pc = 512;
+        m->plan.push_back(op);
+    }
+    {
+        PlanOp op;
+        int rc = plan_conv(m, m->fc, pooled, n, nullptr, nullptr, feat, op);
+        if (rc != PA_OK) return rc;
+        m->plan.push_back(op);
+    }
+    m->plan_crops = crops; m->plan_ws = ws; m->plan_feat = feat; m->plan_n = n;
+    return PA_OK;
+}
+
+extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !crops || !feat || !workspace || n_crops <= 0) return PA_ERR_INVALID_ARG;
+    if (!m->ready) return PA_ERR_NOT_READY;
+    pa_ctx* ctx = m->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->plan_n != n_crops || m->plan_crops != crops || m->plan_ws != workspace || m->plan_feat != feat) {
+        m->plan_n = -1;
+        int rc = build_feature_plan(m, crops, n_crops, feat, workspace, workspace_bytes);
+        if (rc != PA_OK) return rc;
+    }
+    for (const PlanOp& op : m->plan) {
+        int rc = PA_OK;
+        switch (op.kind) {
+            case 0: rc = launch_conv1(op.c1, ctx->num_sms, st); break;
+            case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, st); break;
+            case 2: rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st); break;
+            case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, st); break;
+        }
+        if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "feature kernel launch") : rc;
+        ctx->launches += 1;
+    }
+    return PA_OK;
+}
+
+extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, int n_win, float* logp,
+                       int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m || !feat || !win_idx || !logp || !label || !conf || !workspace || n_feat <= 0 || n_win <= 0) return PA_ERR_INVALID_ARG;
+    if (!m->ready) return PA_ERR_NOT_READY;
+    pa_ctx* ctx = m->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_ws_bytes(m, n_feat) > workspace_bytes) return PA_ERR_WORKSPACE;
+    const bool split = m->precision != PA_PREC_BF16;
+    uint8_t* p = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    Act fb;
+    fb.hi = (bf16*)p; p += align256((size_t)n_feat * 1000 * 2);
+    fb.lo = split ? (bf16*)p : nullptr; p += align256((size_t)n_feat * 1000 * 2);
+    float* proj = (float*)p;
+    if (m->hplan_n != n_feat || m->hplan_feat != feat || m->hplan_ws != workspace) {
+        int rc = plan_conv(m, m->proj, fb, n_feat, nullptr, nullptr, proj, m->head_gemm);
+        if (rc != PA_OK) return rc;
+        m->head_gemm.args.scale = nullptr; m->head_gemm.args.shift = nullptr;
+        m->hplan_n = n_feat; m->hplan_feat = feat; m->hplan_ws = workspace;
+    }
+    int rc = launch_split_f32(feat, fb.hi, fb.lo, (int64_t)n_feat * 1000, st);
+    if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "split launch");
+    const PlanOp& g = m->head_gemm;
+    rc = launch_conv_gemm(g.maps, g.args, g.block_n, g.n_a, g.n_b, ctx->num_sms, st);
+    if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "projection launch") : rc;
+    HeadArgs h;
+    h.proj = proj; h.win_idx = win_idx; h.n_win = n_win; h.n_feat = n_feat; h.seq = m->seq; h.n_actions = m->n_actions;
+    h.b1d = m->b1d; h.w1t = m->w1t; h.b1 = m->b1; h.w2t = m->w2t; h.b2 = m->b2;
+    h.logp = logp; h.label = label; h.conf = conf;
+    rc = launch_head(h, st);
+    if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "head launch") : rc;
+    ctx->launches += 3;
+    return PA_OK;
+}

@@ -1,0 +1,99 @@
+// Internal declarations shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/playaid_b200.h"
+
+namespace pa {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- preprocess
+struct PPParams {
+    const uint8_t* frames;
+    int64_t frames_bytes;
+    int n_frames, H, W;
+    int64_t pitch, fstride;
+    const int32_t* boxes;
+    int n_crops, out, padding, swap_rb;
+    float mean[3], stdv[3];
+    void* outp;
+    int out_dtype, out_layout;
+    int64_t plane_elems;  // distance between the hi and lo planes (PA_DTYPE_BF16X2)
+    int32_t* status;
+    int smem_bytes;
+};
+int launch_preprocess(const PPParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- implicit-GEMM convolution (tcgen05 + TMA)
+// One launch = one convolution / linear layer over all crops, as D[M, Cout] = A[M, K] * W[Cout, K]^T
+// with M = output pixels (NHWC, all crops), K = taps * Cin.
+struct ConvMaps {
+    CUtensorMap a[2][4];  // [plane hi/lo][input parity for stride 2, index 0 for stride 1]
+    CUtensorMap b[2];     // [plane hi/lo] weights [Cout][K] K-major
+};
+
+struct ConvArgs {
+    int m_total;          // valid output rows (pixels)
+    int m_tiles, n_tiles;
+    int cout;             // true output channels (row pitch of the output, in elements)
+    int taps_h, taps_w, stride, pad;
+    int kb_per_tap;       // 64-channel blocks per tap
+    int k_per_tap;        // Cin (K offset between taps in the weight matrix)
+    int ho, wo;           // output spatial size
+    int num_stages;
+    const float* scale;   // [cout] or nullptr (== 1)
+    const float* shift;   // [cout] or nullptr (== 0)
+    const bf16* res_hi;   // residual [M][cout] or nullptr
+    const bf16* res_lo;   // residual lo plane or nullptr
+    int relu;
+    bf16* out_hi;         // bf16 output [M][cout] or nullptr
+    bf16* out_lo;         // lo plane (split precision) or nullptr
+    float* out_f32;       // fp32 output [M][cout] or nullptr
+};
+
+int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms,
+                     cudaStream_t stream);
+size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages);
+int conv_gemm_pick_stages(int block_n, int n_a, int n_b);
+
+// ---------------------------------------------------------------- conv1 (7x7 stride 2, thread-built im2col)
+struct Conv1Args {
+    const bf16* in_hi;    // [n][128][128][4]
+    const bf16* in_lo;    // or nullptr
+    const bf16* w_hi;     // packed [64][256] K-major: k = ky*32 + kx8*4 + c4 (kx8 = kx+1, zero elsewhere)
+    const bf16* w_lo;     // or nullptr (3-MMA mode)
+    const float* scale;   // [64]
+    const float* shift;   // [64]
+    bf16* out_hi;         // [n][64][64][64]
+    bf16* out_lo;         // or nullptr
+    int n_crops;
+};
+int launch_conv1(const Conv1Args& a, int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------- small memory-bound kernels
+int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
+                   cudaStream_t stream);
+int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c,
+                   cudaStream_t stream);
+int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, cudaStream_t stream);
+
+struct HeadArgs {
+    const float* proj;     // [n_feat][seq*512] per-frame temporal projections
+    const int32_t* win_idx;  // [n_win][seq]
+    int n_win, n_feat, seq, n_actions;
+    const float* b1d;      // [512]
+    const float* w1t;      // [512][128] (Linear(512,128) transposed)
+    const float* b1;       // [128]
+    const float* w2t;      // [128][n_actions]
+    const float* b2;       // [n_actions]
+    float* logp;           // [n_win][n_actions]
+    int32_t* label;        // [n_win]
+    float* conf;           // [n_win]
+};
+int launch_head(const HeadArgs& a, cudaStream_t stream);
+
+}  // namespace pa

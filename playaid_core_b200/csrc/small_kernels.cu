@@ -1,0 +1,186 @@
+// Memory-bound helpers of the classifier: 3x3/s2 max-pool, global average pool, fp32 -> bf16
+// hi/lo split, and the temporal head (window gather + MLP + log-softmax / argmax / confidence).
+//
+// References: torchvision resnet18.maxpool / avgpool (via playaid/models/cnn_action_detector.py:16,32);
+// SpatialStreamCNN.cnn1d + classifier (:22-27,37-41); CNNActionDetector.forward log_softmax (:92);
+// AIRunner.action_recognition argmax / exp (playaid/ai_runner.py:474-477).
+#include "pa_internal.cuh"
+
+namespace pa {
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// ---------------------------------------------------------------- maxpool 3x3 stride 2 pad 1 (NHWC, C % 8 == 0)
+__global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                               bf16* __restrict__ out_lo, int n, int hin, int win, int c) {
+    const int ho = hin / 2, wo = win / 2, cg = c / 8;
+    const int64_t total = (int64_t)n * ho * wo * cg;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        int64_t p = i / cg;
+        const int ox = (int)(p % wo); p /= wo;
+        const int oy = (int)(p % ho);
+        const int b = (int)(p / ho);
+        float best[8];
+        uint16_t bh[8], bl[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { best[k] = -INFINITY; bh[k] = 0xFF80; bl[k] = 0; }
+        for (int dy = -1; dy <= 1; dy++) {
+            const int iy = 2 * oy + dy;
+            if (iy < 0 || iy >= hin) continue;
+            for (int dx = -1; dx <= 1; dx++) {
+                const int ix = 2 * ox + dx;
+                if (ix < 0 || ix >= win) continue;
+                const int64_t off = (((int64_t)b * hin + iy) * win + ix) * c + g * 8;
+                const uint4 h = __ldg((const uint4*)(in_hi + off));
+                uint4 l = make_uint4(0, 0, 0, 0);
+                if (in_lo) l = __ldg((const uint4*)(in_lo + off));
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float v0 = bf_lo(hw[k]) + bf_lo(lw[k]), v1 = bf_hi(hw[k]) + bf_hi(lw[k]);
+                    if (v0 > best[2 * k]) { best[2 * k] = v0; bh[2 * k] = (uint16_t)(hw[k] & 0xFFFF); bl[2 * k] = (uint16_t)(lw[k] & 0xFFFF); }
+                    if (v1 > best[2 * k + 1]) { best[2 * k + 1] = v1; bh[2 * k + 1] = (uint16_t)(hw[k] >> 16); bl[2 * k + 1] = (uint16_t)(lw[k] >> 16); }
+                }
+            }
+        }
+        const int64_t o = (((int64_t)b * ho + oy) * wo + ox) * c + g * 8;
+        uint4 oh, ol;
+        oh.x = bh[0] | ((uint32_t)bh[1] << 16); oh.y = bh[2] | ((uint32_t)bh[3] << 16);
+        oh.z = bh[4] | ((uint32_t)bh[5] << 16); oh.w = bh[6] | ((uint32_t)bh[7] << 16);
+        *(uint4*)(out_hi + o) = oh;
+        if (out_lo) {
+            ol.x = bl[0] | ((uint32_t)bl[1] << 16); ol.y = bl[2] | ((uint32_t)bl[3] << 16);
+            ol.z = bl[4] | ((uint32_t)bl[5] << 16); ol.w = bl[6] | ((uint32_t)bl[7] << 16);
+            *(uint4*)(out_lo + o) = ol;
+        }
+    }
+}
+
+int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
+                   cudaStream_t stream) {
+    const int64_t total = (int64_t)n * (hin / 2) * (win / 2) * (c / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    maxpool_kernel<<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- global average pool [n][hw][c] -> [n][c]
+__global__ void avgpool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
+                               bf16* __restrict__ out_lo, int n, int hw, int c) {
+    const int64_t total = (int64_t)n * c;
+    const float inv = 1.f / (float)hw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const int64_t b = i / c;
+        float s = 0.f;
+        for (int p = 0; p < hw; p++) {
+            const int64_t off = (b * hw + p) * c + ch;
+            float v = __bfloat162float(in_hi[off]);
+            if (in_lo) v += __bfloat162float(in_lo[off]);
+            s += v;
+        }
+        s *= inv;
+        const bf16 h = __float2bfloat16_rn(s);
+        out_hi[i] = h;
+        if (out_lo) out_lo[i] = __float2bfloat16_rn(s - __bfloat162float(h));
+    }
+}
+
+int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c, cudaStream_t stream) {
+    const int64_t total = (int64_t)n * c;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    avgpool_kernel<<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- fp32 -> bf16 hi (+ lo)
+__global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = in[i];
+        const bf16 h = __float2bfloat16_rn(v);
+        out_hi[i] = h;
+        if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, cudaStream_t stream) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    split_kernel<<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- temporal head, one CTA (128 threads) per window
+// proj[f][t*512 + o] = sum_i W1d[o][i][t] * feat[f][i]; the Conv1d over a window is the sum over its
+// 7 slots of the matching projection rows (+ bias), so no window tensor is ever built.
+__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
+    __shared__ float h[512];
+    __shared__ float y1[128];
+    __shared__ float y2[128];
+    const int w = blockIdx.x, t = threadIdx.x;
+    const int pitch = a.seq * 512;
+    for (int o = t; o < 512; o += 128) {
+        float s = a.b1d[o];
+        for (int k = 0; k < a.seq; k++) {
+            int f = a.win_idx[(int64_t)w * a.seq + k];
+            f = f < 0 ? 0 : (f >= a.n_feat ? a.n_feat - 1 : f);
+            s += a.proj[(int64_t)f * pitch + k * 512 + o];
+        }
+        h[o] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    {
+        float s = a.b1[t];
+        for (int i = 0; i < 512; i++) s = fmaf(a.w1t[i * 128 + t], h[i], s);
+        y1[t] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    if (t < a.n_actions) {
+        float s = a.b2[t];
+        for (int i = 0; i < 128; i++) s = fmaf(a.w2t[i * a.n_actions + t], y1[i], s);
+        y2[t] = s;
+    }
+    __syncthreads();
+    if (t < 32) {
+        // log-softmax, then argmax over the log-probabilities themselves (first maximum, like
+        // torch.argmax on the reference's output) -- all with warp shuffles (n_actions <= 128)
+        float m = -INFINITY;
+        for (int i = t; i < a.n_actions; i += 32) m = fmaxf(m, y2[i]);
+        for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        float se = 0.f;
+        for (int i = t; i < a.n_actions; i += 32) se += expf(y2[i] - m);
+        for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+        const float lse = m + logf(se);
+        float best = -INFINITY;
+        int bi = 0x7FFFFFFF;
+        for (int i = t; i < a.n_actions; i += 32) {
+            const float lp = y2[i] - lse;
+            a.logp[(int64_t)w * a.n_actions + i] = lp;
+            if (lp > best) { best = lp; bi = i; }
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (t == 0) {
+            a.label[w] = bi;
+            a.conf[w] = expf(best);  // probability; the host multiplies by 100.0 in double like the reference
+        }
+    }
+}
+
+int launch_head(const HeadArgs& a, cudaStream_t stream) {
+    if (a.n_actions > 128 || a.n_win <= 0) return PA_ERR_INVALID_ARG;
+    head_kernel<<<a.n_win, 128, 0, stream>>>(a);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
+}  // namespace pa
