@@ -130,6 +130,20 @@ size_t pa_crop_elems(int out_size);
 int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, int n_win, float* logp,
             int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Single layers (synchronous; scratch allocated and freed inside): one convolution as a tcgen05
+ * implicit GEMM on NHWC bf16 activations [n][hin][hin][cin] (cin % 64 == 0, hin in {32,16,8,4,1} for
+ * the output), and the 7x7/s2 stem on NHWC4 crops. Weights / scale / shift are host fp32 in PyTorch
+ * layout; y = conv(x, w) * scale + shift (+ residual) (ReLU). These are the building blocks
+ * pa_features sequences; exposed for layer-level parity tests against torch.nn.functional.conv2d.
+ * in_lo / out_lo / res_lo may be NULL (plain bf16); split_w != 0 also splits the weights (3 MMAs).
+ */
+int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, int hin, int cin, const float* w_host, int cout,
+              int k, int stride, int pad, const float* scale_host, const float* shift_host, const void* res_hi,
+              const void* res_lo, int relu, void* out_hi, void* out_lo, float* out_f32, int split_w, void* stream);
+int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, const float* w_host, const float* scale_host,
+            const float* shift_host, void* out_hi, void* out_lo, int split_w, void* stream);
+
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t pa_launch_count(pa_ctx* ctx);
 

@@ -169,17 +169,22 @@ static void pil_contain_size(int w, int h, int sw, int sh, int* nw, int* nh) {
 
 /* ImageOps.pad(img, (sw, sh), color="black"): contain + BICUBIC + centred paste. */
 int pa_oracle_pil_pad(const uint8_t* src, int h, int w, int src_pitch, uint8_t* dst, int sh, int sw) {
-    if (h <= 0 || w <= 0) return PA_INVALID; /* Image.fromarray of an empty array raises */
-    if (sh == 0) return PA_ERR_ZERO_DIV;      /* dest_ratio = size[0] / size[1] */
+    if (h <= 0) return PA_ERR_ZERO_DIV;  /* contain(): im_ratio = image.width / image.height */
+    if (sh == 0) return PA_ERR_ZERO_DIV; /* dest_ratio = size[0] / size[1] */
+    if (w < 0 || sw <= 0) return PA_INVALID;
     int nw, nh;
     pil_contain_size(w, h, sw, sh, &nw, &nh);
-    if (nw <= 0 || nh <= 0 || sw <= 0) return PA_INVALID;
+    /* Image.resize: identical size -> copy() (even for an empty image); otherwise the C resampler
+       raises ValueError("height and width must be > 0") for an empty target */
+    const int same = (nw == w && nh == h);
+    if (!same && (nw <= 0 || nh <= 0)) return PA_INVALID;
     if (nw == sw && nh == sh) return pa_oracle_pil_bicubic(src, h, w, src_pitch, dst, sh, sw);
+    memset(dst, 0, (size_t)sw * sh * 3);
+    if (nw <= 0 || nh <= 0) return PA_OK; /* empty paste: black canvas */
     uint8_t* res = (uint8_t*)malloc((size_t)nw * nh * 3);
     if (!res) return PA_ERR_ALLOC;
     int rc = pa_oracle_pil_bicubic(src, h, w, src_pitch, res, nh, nw);
     if (rc != PA_OK) { free(res); return rc; }
-    memset(dst, 0, (size_t)sw * sh * 3);
     int ox = 0, oy = 0;
     if (nw != sw) ox = (int)rint((sw - nw) * 0.5);
     else oy = (int)rint((sh - nh) * 0.5);
@@ -382,8 +387,7 @@ int pa_oracle_square_crop(const uint8_t* image, int H, int W, int pitch, int cx,
     int raw_pitch = pitch;
     uint8_t* sq = NULL;
     if (rh != sd || rw != sd) {
-        if (rh == 0 || rw == 0) return PA_INVALID; /* Image.fromarray raises ValueError on an empty array */
-        if (sd == 0) return PA_ERR_ZERO_DIV;
+        if (rh == 0 || sd == 0) return PA_ERR_ZERO_DIV; /* contain(): width / height, size[0] / size[1] */
         sq = (uint8_t*)malloc((size_t)sd * sd * 3);
         if (!sq) return PA_ERR_ALLOC;
         int rc = pa_oracle_pil_pad(raw, rh, rw, pitch, sq, sd, sd);

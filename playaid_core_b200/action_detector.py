@@ -1,0 +1,160 @@
+"""`ActionDetector`: the ult_logger-driven crop -> classify path, end to end on one GPU.
+
+The reference spreads this path over an offline script and a deprecated runner
+(SURVEY.md 3.2): `process_pairing` (playaid/data_gen_scripts/gen_gt_action_detection.py:26-91)
+crops every fighter with `square_crop(frame, 128, padding=30)`; `AIRunner`
+(playaid/ai_runner.py:426-520) builds a 7-frame middle-out window per (frame, fighter), runs
+`CNNActionDetector`, takes argmax / exp and fills
+`ai_output_data[fighter][frame] = {crop, action, predicted_action_confidence}` which
+`write_output` dumps as ai_output.yaml (:606-608) for `load_timeline_from_ai_output`
+(playaid/timeline.py:52-105). This module composes the same steps on the GPU:
+
+    boxes (host fp64, fighter.py geometry) -> pa_preprocess -> pa_features (once per crop)
+    -> feature table -> pa_head over middle-out windows -> labels / log-probs / confidence
+
+`MatchStream` feeds a long match in chunks (frames need not be resident all at once); windows
+reach +-27 frames (delta 3), so labels trail the pushed frames by 27.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import yaml
+
+from . import _lib
+from .dataset_utils import window_index_table
+from .fighter import YoloCrop, boxes_from_timeline
+from .models.cnn_action_detector import CNNActionDetector
+from .preprocess import crop_records, preprocess_crops
+
+
+class MatchStream:
+    """Streaming state for one match: feature table + how far crops / labels have progressed."""
+
+    def __init__(self, det: "ActionDetector", total_frames: int, n_fighters: int, H: int, W: int):
+        self.det, self.N, self.F, self.H, self.W = det, int(total_frames), int(n_fighters), int(H), int(W)
+        dev = det.model._device
+        A = det.model.num_actions
+        self.feat = torch.zeros((self.N * self.F, 1000), dtype=torch.float32, device=dev)
+        self.logp = torch.empty((self.N, self.F, A), dtype=torch.float32, device=dev)
+        self.label = torch.full((self.N, self.F), -1, dtype=torch.int32, device=dev)
+        self.prob = torch.zeros((self.N, self.F), dtype=torch.float32, device=dev)
+        self.status = torch.zeros((self.N, self.F), dtype=torch.int32, device=dev)
+        self.pushed = 0   # frames whose features are in the table
+        self.labeled = 0  # frames whose windows have been classified
+        # all window indices of the match, as frame numbers (host) -- dataset_utils.py:109-138
+        self.win_frames = window_index_table(
+            np.arange(det.min_frame, self.N), det.num_frames_per_sample, det.frame_delta, max_frames=self.N,
+            min_frame=det.min_frame,
+        )
+        mid = det.num_frames_per_sample // 2
+        self.reach = det.frame_delta * mid * mid
+
+    def push(self, frames: torch.Tensor, boxes: np.ndarray) -> tuple[int, int]:
+        """frames uint8 CUDA [n,H,W,3] for match frames [pushed, pushed+n); boxes float64 [n,F,4].
+        Returns the [a, b) range of frames labelled by this call."""
+        det = self.det
+        n = int(frames.shape[0])
+        f0 = self.pushed
+        assert boxes.shape[:2] == (n, self.F) and f0 + n <= self.N
+        rec = crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(n), self.F), self.W, self.H)
+        rec_d = torch.from_numpy(rec).to(frames.device, non_blocking=True)
+        crops, status = preprocess_crops(
+            frames, rec_d, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
+            dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4, out=det._crop_buffer(n * self.F),
+        )
+        self.status[f0 : f0 + n] = status.view(n, self.F)
+        det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
+        self.pushed = f0 + n
+        return self._label_ready()
+
+    def _label_ready(self) -> tuple[int, int]:
+        det = self.det
+        a = self.labeled
+        b = self.N if self.pushed == self.N else max(a, self.pushed - self.reach)
+        a = max(a, det.min_frame)
+        if b <= a:
+            return (a, a)
+        # feature rows needed by windows centred on [a, b)
+        wf = self.win_frames[a - det.min_frame : b - det.min_frame]  # [nb, S] frame numbers
+        lo, hi = int(wf.min()), int(wf.max()) + 1
+        idx = (wf[:, None, :] - lo) * self.F + np.arange(self.F)[None, :, None]  # [nb, F, S] rows rel. to lo*F
+        idx_d = torch.from_numpy(np.ascontiguousarray(idx.reshape(-1, wf.shape[1]).astype(np.int32))).to(self.feat.device)
+        logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx_d)
+        self.logp[a:b] = logp.view(b - a, self.F, -1)
+        self.label[a:b] = label.view(b - a, self.F)
+        self.prob[a:b] = prob.view(b - a, self.F)
+        self.labeled = b
+        return (a, b)
+
+
+class ActionDetector:
+    def __init__(
+        self,
+        model: CNNActionDetector,
+        output_size: int = 128,
+        padding: int = 30,
+        num_frames_per_sample: int | None = None,
+        frame_delta: int = 3,
+        min_frame: int = 0,
+        mean=(0.0, 0.0, 0.0),
+        std=(1.0, 1.0, 1.0),
+    ):
+        self.model = model
+        self.output_size = output_size
+        self.padding = padding
+        self.num_frames_per_sample = num_frames_per_sample or model.sequence_length
+        assert self.num_frames_per_sample == model.sequence_length, "window length must equal the Conv1d kernel"
+        self.frame_delta = frame_delta
+        self.min_frame = min_frame
+        self.mean, self.std = tuple(mean), tuple(std)
+        self._crops: torch.Tensor | None = None
+
+    def _crop_buffer(self, n: int) -> torch.Tensor:
+        planes = 2 if self.model.split else 1
+        shape = (planes, n, self.output_size, self.output_size, 4) if planes == 2 else (n, self.output_size, self.output_size, 4)
+        if self._crops is None or tuple(self._crops.shape) != shape:
+            self._crops = torch.empty(shape, dtype=torch.bfloat16, device=self.model._device)
+        return self._crops
+
+    def stream(self, total_frames: int, n_fighters: int, H: int, W: int) -> MatchStream:
+        return MatchStream(self, total_frames, n_fighters, H, W)
+
+    def classify_clip(self, frames: torch.Tensor, boxes: np.ndarray, chunk: int = 256) -> dict:
+        """frames uint8 CUDA [N,H,W,3] (BGR, as decoded by cv2), boxes float64 [N,F,4] normalised.
+        Returns device tensors: label [N,F] int32, logp [N,F,A], prob [N,F], status [N,F]."""
+        N, H, W, _ = frames.shape
+        st = self.stream(N, boxes.shape[1], H, W)
+        for s in range(0, N, chunk):
+            st.push(frames[s : s + chunk], boxes[s : s + chunk])
+        return {"label": st.label, "logp": st.logp, "prob": st.prob, "status": st.status}
+
+    def classify_timeline(self, frames: torch.Tensor, timeline, chunk: int = 256) -> dict:
+        """`timeline` = `load_ground_truth_from_path(log)` records; boxes via the fighter geometry."""
+        return self.classify_clip(frames, boxes_from_timeline(timeline)[: frames.shape[0]], chunk)
+
+    # ------------------------------------------------------------------ ai_output.yaml (ai_runner.py:493-520,606-608)
+    def ai_output(self, result: dict, boxes: np.ndarray, fighter_names: list[str]) -> dict:
+        """{fighter: {frame_idx: {crop, action, predicted_action_confidence}}} like AIRunner's
+        `ai_output_data.to_dict()`; confidence = float(exp(logp)[label]) * 100.0 (ai_runner.py:476-477)."""
+        label = result["label"].cpu().numpy()
+        prob = result["prob"].cpu().numpy()
+        out = {}
+        for k, name in enumerate(fighter_names):
+            per = {}
+            for i in range(label.shape[0]):
+                if label[i, k] < 0:
+                    continue
+                c = YoloCrop(*[float(v) for v in boxes[i, k]])
+                per[i] = {
+                    "crop": str(c),
+                    "action": self.model.actions[int(label[i, k])],
+                    "predicted_action_confidence": float(prob[i, k]) * 100.0,
+                }
+            out[name] = per
+        return out
+
+    @staticmethod
+    def write_output(ai_output: dict, path: str) -> None:
+        with open(path, "w") as f:
+            yaml.dump(ai_output, f)

@@ -628,3 +628,90 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
     ctx->launches += 3;
     return PA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ single-layer entry points
+// One convolution / the stem on caller-provided NHWC bf16 activations and host fp32 weights.
+// Used by the layer-level parity tests (tests/test_gpu_layers.py); synchronous, allocates scratch.
+static int layer_model(pa_ctx* ctx, int split_w, pa_model& m) {
+    m.ctx = ctx;
+    m.precision = split_w ? PA_PREC_BF16X3 : PA_PREC_BF16;
+    return PA_OK;
+}
+
+extern "C" int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, int hin, int cin, const float* w_host,
+                         int cout, int k, int stride, int pad, const float* scale_host, const float* shift_host,
+                         const void* res_hi, const void* res_lo, int relu, void* out_hi, void* out_lo, float* out_f32,
+                         int split_w, void* stream) {
+    if (!ctx || !in_hi || !w_host || n <= 0 || (!out_hi && !out_f32)) return PA_ERR_INVALID_ARG;
+    if (split_w && !in_lo) return PA_ERR_INVALID_ARG;
+    pa_model m;
+    layer_model(ctx, split_w, m);
+    HostTensor t;
+    t.shape = {cout, cin, k, k};
+    t.data.assign(w_host, w_host + (size_t)cout * cin * k * k);
+    m.tensors["w"] = t;
+    ConvLayer L = make_conv("w", "", cin, cout, k, stride, pad, hin, relu != 0);
+    int rc = prepare_conv(&m, L);
+    if (rc == PA_OK) {
+        if (scale_host) cudaMemcpy(L.scale, scale_host, cout * sizeof(float), cudaMemcpyHostToDevice);
+        if (shift_host) cudaMemcpy(L.shift, shift_host, cout * sizeof(float), cudaMemcpyHostToDevice);
+        Act in, res, out;
+        in.hi = (bf16*)in_hi; in.lo = (bf16*)in_lo;
+        res.hi = (bf16*)res_hi; res.lo = (bf16*)res_lo;
+        out.hi = (bf16*)out_hi; out.lo = (bf16*)out_lo;
+        PlanOp op;
+        rc = plan_conv(&m, L, in, n, res_hi ? &res : nullptr, out_hi ? &out : nullptr, out_f32, op);
+        if (rc == PA_OK) rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, (cudaStream_t)stream);
+        if (rc == PA_OK) {
+            ctx->launches += 1;
+            cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "pa_conv2d");
+        } else if (rc == PA_ERR_CUDA) {
+            cuda_fail(ctx, cudaGetLastError(), "pa_conv2d launch");
+        }
+    }
+    for (void* p : m.dev_allocs) cudaFree(p);
+    m.dev_allocs.clear();
+    return rc;
+}
+
+extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, const float* w_host /*[64][3][7][7]*/,
+                       const float* scale_host, const float* shift_host, void* out_hi, void* out_lo, int split_w, void* stream) {
+    if (!ctx || !in_hi || !w_host || !scale_host || !shift_host || !out_hi || n <= 0) return PA_ERR_INVALID_ARG;
+    if (split_w && !in_lo) return PA_ERR_INVALID_ARG;
+    pa_model m;
+    layer_model(ctx, split_w, m);
+    std::vector<float> packed((size_t)64 * 256, 0.f);
+    for (int o = 0; o < 64; o++)
+        for (int c = 0; c < 3; c++)
+            for (int ky = 0; ky < 7; ky++)
+                for (int kx = 0; kx < 7; kx++)
+                    packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w_host[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
+    std::vector<uint16_t> hi, lo;
+    split_weights(packed, hi, lo);
+    std::vector<float> sc(scale_host, scale_host + 64), sh(shift_host, shift_host + 64);
+    Conv1Args a;
+    memset(&a, 0, sizeof(a));
+    int rc = upload(&m, hi, (uint16_t**)&a.w_hi);
+    if (rc == PA_OK && split_w) rc = upload(&m, lo, (uint16_t**)&a.w_lo);
+    float *dsc = nullptr, *dsh = nullptr;
+    if (rc == PA_OK) rc = upload(&m, sc, &dsc);
+    if (rc == PA_OK) rc = upload(&m, sh, &dsh);
+    if (rc == PA_OK) {
+        a.in_hi = (const bf16*)in_hi; a.in_lo = (const bf16*)in_lo;
+        a.scale = dsc; a.shift = dsh;
+        a.out_hi = (bf16*)out_hi; a.out_lo = (bf16*)out_lo;
+        a.n_crops = n;
+        rc = launch_conv1(a, ctx->num_sms, (cudaStream_t)stream);
+        if (rc == PA_OK) {
+            ctx->launches += 1;
+            cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "pa_stem");
+        } else if (rc == PA_ERR_CUDA) {
+            cuda_fail(ctx, cudaGetLastError(), "pa_stem launch");
+        }
+    }
+    for (void* p : m.dev_allocs) cudaFree(p);
+    m.dev_allocs.clear();
+    return rc;
+}

@@ -136,11 +136,13 @@ __device__ void compute_geom(CropGeom& g, const int32_t* box, int H, int W, int 
     g.pad1 = (rh != sd || rw != sd);
     g.nw = sd; g.nh = sd; g.ox = 0; g.oy = 0; g.hact = 0; g.vact = 0;
     if (g.pad1) {
-        if (rh == 0 || rw == 0) { g.status = PA_CROP_INVALID; return; }
-        if (sd == 0) { g.status = PA_CROP_ZERO_DIV; return; }
+        // ImageOps.contain divides width / height and size[0] / size[1]: ZeroDivisionError escapes
+        if (rh == 0 || sd == 0) { g.status = PA_CROP_ZERO_DIV; return; }
         int nw, nh;
         contain_size(rw, rh, sd, sd, nw, nh);
-        if (nw <= 0 || nh <= 0) { g.status = PA_CROP_INVALID; return; }
+        // Image.resize copies when the size is unchanged (even an empty image -> black canvas);
+        // otherwise an empty target raises ValueError -> (False, None)
+        if (!(nw == rw && nh == rh) && (nw <= 0 || nh <= 0)) { g.status = PA_CROP_INVALID; return; }
         g.nw = nw; g.nh = nh;
         if (!(nw == sd && nh == sd)) {
             if (nw != sd) g.ox = rint_d((double)(sd - nw) * 0.5);
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
 
         // ---------------- load raw rows [t0, t1): 128-bit reads of the 16-byte-aligned cover
         int shift = 0;
-        if (nt > 0) {
+        if (nt > 0 && rw > 0) {
             const int64_t row0 = (int64_t)g.y0 * p.pitch + (int64_t)g.x0 * 3;
             if (vec_ok) {
                 shift = (int)(row0 & 15);

@@ -1,0 +1,215 @@
+"""`CNNActionDetector` on B200: drop-in for reference playaid/models/cnn_action_detector.py.
+
+Same constructor arguments, attributes (`actions`, `num_actions`, `sequence_length`, `model`),
+`load_from_checkpoint(path, actions=...)` (Lightning checkpoint: `ckpt["state_dict"]`, keys
+`model.cnn2d.*`, `model.cnn1d.0.*`, `model.classifier.{0,2}.*`), `eval()`, and
+`forward(x[B,S,3,128,128] in [0,1], RGB) -> [B, len(actions)]` log-probabilities
+(reference :46-92). The arithmetic runs in the hand-written sm_100a kernels behind
+`pa_features` / `pa_head`; inference only (training steps and dataloaders are out of scope).
+
+Beyond the reference surface, `features()` / `head()` expose the two halves separately so that
+callers can compute ResNet-18 features once per (frame, fighter) and reuse them across the seven
+windows that contain a frame (the reference recomputes them 7x, playaid/ai_runner.py:493-520).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+PRECISIONS = {"bf16": _lib.PREC_BF16, "bf16x2": _lib.PREC_BF16X2, "bf16x3": _lib.PREC_BF16X3}
+
+
+class SpatialStreamCNN:
+    """Holds the weights (host fp32 state_dict) and the native model handle."""
+
+    def __init__(self, num_actions: int, sequence_length: int):
+        self.num_actions = num_actions
+        self.sequence_length = sequence_length
+        self._state: dict[str, torch.Tensor] = {}
+
+    def state_dict(self):
+        return dict(self._state)
+
+
+class CNNActionDetector:
+    def __init__(
+        self,
+        actions: list,
+        batch_size: int = 64,
+        sequence_length: int = 4,
+        learning_rate: float = 2e-4,
+        num_samples: int = 1024,
+        freeze_encoder=False,
+        precision: str = "bf16",
+        device=None,
+        **kwargs,
+    ):
+        self.learning_rate = learning_rate
+        self.batch_size = batch_size
+        self.actions = list(actions)
+        self.num_actions = len(self.actions)
+        self.num_samples = num_samples
+        self.sequence_length = sequence_length
+        self.dataset_kwargs = kwargs
+        self.model = SpatialStreamCNN(self.num_actions, self.sequence_length)
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        self.training = False
+        self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self._ctx = None
+        self._handle = None
+        self._ws: torch.Tensor | None = None
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Accepts the reference's keys with or without the Lightning `model.` prefix."""
+        sd = {}
+        for k, v in state_dict.items():
+            if k.endswith("num_batches_tracked") or "accuracy" in k:
+                continue
+            sd[k[6:] if k.startswith("model.") else k] = v.detach().to("cpu", torch.float32).contiguous()
+        self.model._state = sd
+        self._finalize()
+        return self
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, actions=None, map_location=None, **kwargs):
+        ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(kwargs)
+        if actions is not None:
+            hp["actions"] = actions
+        sd = ckpt["state_dict"]
+        if "sequence_length" not in hp:
+            key = "model.cnn1d.0.weight" if "model.cnn1d.0.weight" in sd else "cnn1d.0.weight"
+            hp["sequence_length"] = int(sd[key].shape[2])
+        obj = cls(**hp)
+        obj.load_state_dict(sd)
+        return obj
+
+    def state_dict(self):
+        return {"model." + k: v for k, v in self.model._state.items()}
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("playaid_core_b200 is inference-only (training is out of scope)")
+        return self.eval()
+
+    def to(self, device):
+        self._device = torch.device(device)
+        if self.model._state:
+            self._finalize()
+        return self
+
+    def _finalize(self):
+        if self._device.type != "cuda":
+            raise _lib.PlayaidLibraryError("CNNActionDetector needs a CUDA device (no CPU path)")
+        self._ctx = _lib.Context.get(self._device)
+        lib = self._ctx.lib
+        if self._handle is not None:
+            lib.pa_model_destroy(self._handle)
+            self._handle = None
+        h = ctypes.c_void_p()
+        _lib.check(lib.pa_model_create(self._ctx.handle, self.num_actions, self.sequence_length, ctypes.byref(h)),
+                   self._ctx.handle, "pa_model_create")
+        for k, v in self.model._state.items():
+            a = v.numpy()
+            shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+            _lib.check(lib.pa_model_set_tensor(h, k.encode(), a.ctypes.data, shape, a.ndim), self._ctx.handle, f"set_tensor {k}")
+        with torch.cuda.device(self._device):
+            _lib.check(lib.pa_model_finalize(h, PRECISIONS[self.precision]), self._ctx.handle, "pa_model_finalize")
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if self._handle is not None and self._ctx is not None:
+                self._ctx.lib.pa_model_destroy(self._handle)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ native halves
+    @property
+    def split(self) -> bool:
+        return self.precision != "bf16"
+
+    @property
+    def crop_dtype(self) -> int:
+        """pa_preprocess out_dtype that matches this model's arithmetic."""
+        return _lib.DTYPE_BF16X2 if self.split else _lib.DTYPE_BF16
+
+    def _workspace(self, n: int) -> torch.Tensor:
+        need = ctypes.c_size_t()
+        _lib.check(self._ctx.lib.pa_model_workspace_bytes(self._handle, n, ctypes.byref(need)), self._ctx.handle, "workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value:
+            self._ws = torch.empty((need.value,), dtype=torch.uint8, device=self._device)
+        return self._ws
+
+    def features(self, crops: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """crops: bf16 CUDA NHWC4 [n,128,128,4] (or [2,n,128,128,4] hi/lo planes in split precision),
+        as written by `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4)` -> fp32 [n,1000]."""
+        if self._handle is None:
+            raise _lib.PlayaidLibraryError("no weights loaded: call load_state_dict / load_from_checkpoint first")
+        want = 5 if self.split else 4
+        if crops.dtype != torch.bfloat16 or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 128, 4):
+            raise ValueError("crops must be contiguous bf16 NHWC4 [n,128,128,4] ([2,n,...] planes in split precision)")
+        n = int(crops.shape[-4])
+        if out is None:
+            out = torch.empty((n, 1000), dtype=torch.float32, device=crops.device)
+        ws = self._workspace(n)
+        with torch.cuda.device(crops.device):
+            rc = self._ctx.lib.pa_features(self._handle, crops.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           _lib.current_stream_ptr(crops.device))
+        _lib.check(rc, self._ctx.handle, "pa_features")
+        return out
+
+    def head(self, feat: torch.Tensor, win_idx: torch.Tensor):
+        """feat fp32 [n_feat,1000], win_idx int32 [n_win,S] rows of feat ->
+        (logp [n_win,A] fp32, label [n_win] int32, prob [n_win] fp32)."""
+        if self._handle is None:
+            raise _lib.PlayaidLibraryError("no weights loaded")
+        if feat.dtype != torch.float32 or not feat.is_contiguous() or feat.shape[-1] != 1000:
+            raise ValueError("feat must be contiguous fp32 [n,1000]")
+        if win_idx.dtype != torch.int32 or not win_idx.is_contiguous() or win_idx.shape[-1] != self.sequence_length:
+            raise ValueError("win_idx must be contiguous int32 [n_win, sequence_length]")
+        n_feat, n_win = int(feat.shape[0]), int(win_idx.shape[0])
+        logp = torch.empty((n_win, self.num_actions), dtype=torch.float32, device=feat.device)
+        label = torch.empty((n_win,), dtype=torch.int32, device=feat.device)
+        prob = torch.empty((n_win,), dtype=torch.float32, device=feat.device)
+        ws = self._workspace(max(n_feat, 1))
+        with torch.cuda.device(feat.device):
+            rc = self._ctx.lib.pa_head(self._handle, feat.data_ptr(), n_feat, win_idx.data_ptr(), n_win, logp.data_ptr(),
+                                       label.data_ptr(), prob.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _lib.current_stream_ptr(feat.device))
+        _lib.check(rc, self._ctx.handle, "pa_head")
+        return logp, label, prob
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [B,S,3,H,W] float in [0,1] (RGB, as built at ai_runner.py:461-463) -> log-probs [B,A]."""
+        B, S, C, H, W = x.shape
+        if S != self.sequence_length or C != 3 or H != 128 or W != 128:
+            raise ValueError(f"expected [B,{self.sequence_length},3,128,128], got {tuple(x.shape)}")
+        x = x.to(self._device, torch.float32).reshape(B * S, 3, H, W).permute(0, 2, 3, 1)
+        x4 = torch.zeros((B * S, H, W, 4), dtype=torch.float32, device=self._device)
+        x4[..., :3] = x
+        hi = x4.to(torch.bfloat16)
+        if self.split:
+            lo = (x4 - hi.float()).to(torch.bfloat16)
+            crops = torch.stack([hi, lo]).contiguous()
+        else:
+            crops = hi.contiguous()
+        feat = self.features(crops)
+        idx = torch.arange(B * S, dtype=torch.int32, device=self._device).reshape(B, S).contiguous()
+        logp, _, _ = self.head(feat, idx)
+        return logp
+
+    __call__ = forward

@@ -1,0 +1,169 @@
+"""Layer-level parity of the tcgen05 implicit-GEMM kernels (pa_conv2d / pa_stem through the C-ABI)
+against torch.nn.functional.conv2d in fp32 on the same bf16-rounded operands.
+
+Tolerances: operands are exactly representable, so the only difference is fp32 accumulation
+order -> |err| <= 2e-3 * max|ref| for plain bf16 outputs read back in fp32 (pa_conv2d's fp32
+output), and bf16 rounding (2^-8 relative) for bf16 outputs.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    assert torch.cuda.is_available()
+    from playaid_core_b200 import _lib
+
+    return torch, _lib, _lib.Context.get(0)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _conv(env, x, w, stride, pad, scale=None, shift=None, res=None, relu=False, split=False, out_bf16=False, split_w=False):
+    """x [N,C,H,W] fp32 (bf16-representable unless split), w [O,C,k,k] fp32. Returns NCHW fp32."""
+    torch, _lib, ctx = env
+    N, C, H, _ = x.shape
+    O, _, k, _ = w.shape
+    Ho = H // stride
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    hi = xh.to(torch.bfloat16)
+    lo = (xh - hi.float()).to(torch.bfloat16) if split else None
+    rh = rl = None
+    if res is not None:
+        r = res.permute(0, 2, 3, 1).contiguous()
+        rh = r.to(torch.bfloat16)
+        rl = (r - rh.float()).to(torch.bfloat16) if split else None
+    out_f32 = None if out_bf16 else torch.full((N, Ho, Ho, O), float("nan"), device="cuda")
+    out_hi = torch.full((N, Ho, Ho, O), float("nan"), device="cuda", dtype=torch.bfloat16) if out_bf16 else None
+    out_lo = torch.zeros_like(out_hi) if (out_bf16 and split) else None
+    wc = w.cpu().contiguous()
+    sc = scale.cpu().contiguous() if scale is not None else None
+    sh = shift.cpu().contiguous() if shift is not None else None
+    rc = ctx.lib.pa_conv2d(ctx.handle, _ptr(hi), _ptr(lo), N, H, C, wc.data_ptr(), O, k, stride, pad,
+                           sc.data_ptr() if sc is not None else None, sh.data_ptr() if sh is not None else None,
+                           _ptr(rh), _ptr(rl), 1 if relu else 0, _ptr(out_hi), _ptr(out_lo), _ptr(out_f32), 1 if split_w else 0,
+                           _lib.current_stream_ptr())
+    _lib.check(rc, ctx.handle, "pa_conv2d")
+    torch.cuda.synchronize()
+    if out_bf16:
+        y = out_hi.float() + (out_lo.float() if out_lo is not None else 0)
+    else:
+        y = out_f32
+    return y.permute(0, 3, 1, 2)
+
+
+def _ref(torch, x, w, stride, pad, scale=None, shift=None, res=None, relu=False):
+    y = torch.nn.functional.conv2d(x.double(), w.double(), stride=stride, padding=pad)
+    if scale is not None:
+        y = y * scale.double().view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + shift.double().view(1, -1, 1, 1)
+    if res is not None:
+        y = y + res.double()
+    if relu:
+        y = torch.relu(y)
+    return y.float()
+
+
+def _bf(torch, t):
+    return t.to(torch.bfloat16).float()
+
+
+CASES = [
+    # (N, Cin, H, Cout, k, stride, pad)  -- every geometry ResNet-18 @128x128 uses
+    (3, 64, 32, 64, 3, 1, 1),      # layer1
+    (2, 64, 32, 128, 3, 2, 1),     # layer2.0.conv1
+    (2, 64, 32, 128, 1, 2, 0),     # layer2.0.downsample
+    (3, 128, 16, 128, 3, 1, 1),    # layer2
+    (3, 128, 16, 256, 3, 2, 1),    # layer3.0.conv1 (8x8 out, 2 crops per tile, odd batch)
+    (5, 256, 8, 256, 3, 1, 1),     # layer3
+    (9, 256, 8, 512, 3, 2, 1),     # layer4.0.conv1 (4x4 out, 8 crops per tile, ragged)
+    (9, 256, 8, 512, 1, 2, 0),     # layer4.0.downsample
+    (11, 512, 4, 512, 3, 1, 1),    # layer4
+    (130, 512, 1, 1000, 1, 1, 0),  # fc (N tiles masked at 1000, M ragged)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_bf16_vs_torch(env, case):
+    torch = env[0]
+    N, C, H, O, k, s, p = case
+    g = torch.Generator(device="cuda").manual_seed(hash(case) % 2**31)
+    x = _bf(torch, torch.randn((N, C, H, H), device="cuda", generator=g))
+    w = _bf(torch, torch.randn((O, C, k, k), device="cuda", generator=g) / (C * k * k) ** 0.5)
+    y = _conv(env, x, w, s, p)
+    ref = _ref(torch, x, w, s, p)
+    assert torch.isfinite(y).all()
+    err = float((y - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-3, err
+
+
+def test_conv_epilogue_scale_shift_residual_relu(env):
+    torch = env[0]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = _bf(torch, torch.randn((4, 64, 32, 32), device="cuda", generator=g))
+    w = _bf(torch, torch.randn((64, 64, 3, 3), device="cuda", generator=g) / 24)
+    res = _bf(torch, torch.randn((4, 64, 32, 32), device="cuda", generator=g))
+    scale = torch.rand(64, device="cuda", generator=g) + 0.5
+    shift = torch.randn(64, device="cuda", generator=g)
+    y = _conv(env, x, w, 1, 1, scale, shift, res, relu=True)
+    ref = _ref(torch, x, w, 1, 1, scale, shift, res, relu=True)
+    assert float((y - ref).abs().max()) / float(ref.abs().max()) < 2e-3
+    yb = _conv(env, x, w, 1, 1, scale, shift, res, relu=True, out_bf16=True)
+    assert float((yb - ref).abs().max()) / float(ref.abs().max()) < 1e-2
+    assert float(yb.min()) >= 0.0
+
+
+def test_conv_split_precision_is_fp32_accurate(env):
+    """hi+lo activations with bf16-exact weights (PA_PREC_BF16X2) and split weights (X3)."""
+    torch = env[0]
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn((3, 128, 16, 16), device="cuda", generator=g)           # NOT bf16-representable
+    w = _bf(torch, torch.randn((128, 128, 3, 3), device="cuda", generator=g) / 34)
+    ref = _ref(torch, x, w, 1, 1)
+    y1 = _conv(env, _bf(torch, x), w, 1, 1)
+    y2 = _conv(env, x, w, 1, 1, split=True)
+    e1 = float((y1 - ref).abs().max()) / float(ref.abs().max())
+    e2 = float((y2 - ref).abs().max()) / float(ref.abs().max())
+    assert e2 < 3e-5 and e2 < e1 / 20, (e1, e2)
+    w32 = torch.randn((128, 128, 3, 3), device="cuda", generator=g) / 34     # arbitrary fp32 weights
+    ref3 = _ref(torch, x, w32, 1, 1)
+    y3 = _conv(env, x, w32, 1, 1, split=True, split_w=True)
+    assert float((y3 - ref3).abs().max()) / float(ref3.abs().max()) < 5e-5
+    yb = _conv(env, x, w, 1, 1, split=True, out_bf16=True)                    # hi+lo output planes
+    assert float((yb - ref).abs().max()) / float(ref.abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_stem_vs_torch(env, split):
+    torch, _lib, ctx = env
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N = 5
+    x = torch.rand((N, 3, 128, 128), device="cuda", generator=g)
+    if not split:
+        x = _bf(torch, x)
+    w = _bf(torch, torch.randn((64, 3, 7, 7), device="cuda", generator=g) / 12)
+    scale = torch.rand(64, device="cuda", generator=g) + 0.5
+    shift = torch.randn(64, device="cuda", generator=g) * 0.1
+    x4 = torch.zeros((N, 128, 128, 4), device="cuda")
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    hi = x4.to(torch.bfloat16)
+    lo = (x4 - hi.float()).to(torch.bfloat16) if split else None
+    out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out_lo = torch.zeros_like(out_hi) if split else None
+    rc = ctx.lib.pa_stem(ctx.handle, _ptr(hi), _ptr(lo), N, w.cpu().contiguous().data_ptr(), scale.cpu().data_ptr(),
+                         shift.cpu().data_ptr(), _ptr(out_hi), _ptr(out_lo), 0, _lib.current_stream_ptr())
+    _lib.check(rc, ctx.handle, "pa_stem")
+    torch.cuda.synchronize()
+    y = (out_hi.float() + (out_lo.float() if split else 0)).permute(0, 3, 1, 2)
+    ref = _ref(torch, x, w, 2, 3, scale, shift, relu=True)
+    err = float((y - ref).abs().max()) / float(ref.abs().max())
+    assert torch.isfinite(y).all() and err < (5e-5 if split else 1e-2), err
