@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the fighter action-recognition hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one 256-frame batch of the synthetic 3-minute 1080p match (2 fighters -> 512 crops)
+through crop -> resize -> normalise -> ResNet-18 features -> temporal head -> labels
+(BASELINE.json configs[1]). Prints ONE JSON line (see the task contract):
+
+* value     frames/s with the batch's frames already resident in HBM (device-timed, max over ranks)
+* e2e       frames/s through the public API from HOST buffers: pinned host frames -> H2D -> same
+            kernels -> labels/probabilities D2H, copies inside the timed region
+* roofline  the dominant kernel's achieved rate vs the measured peak in MEASURED_PEAKS.json, from
+            per-kernel CUDA-event timing (pa_profile_begin/end) inside this script
+* cpu_baseline  the CPU oracle port (oracle/ref_path.py: cv2 + Pillow + torch CPU, all host threads)
+            timed on a bounded sample of the same workload on this box
+
+`--impl reference` times that CPU port alone (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec (1080p, 2 fighters, crop->classify)"
+UNIT = "frames/s"
+BATCH_FRAMES = 256
+N_FIGHTERS = 2
+MATCH_FRAMES = 10800  # 3 minutes at 60 fps
+H, W = 1080, 1920
+N_RESIDENT = 4  # distinct 256-frame batches kept in HBM and cycled (each 1.59 GB >> 126 MB L2)
+
+# algorithmic work
+FLOP_PER_CROP = 2 * 592_695_296
+FLOP_HEAD_PER_WINDOW = 2 * 3_657_600
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def match_boxes(seed: int):
+    from playaid_core_b200.fighter import boxes_from_records
+    from workloads import synthetic
+
+    recs = synthetic.synth_log_records(MATCH_FRAMES, N_FIGHTERS, seed=seed)
+    return boxes_from_records([r for f in recs for r in f]).reshape(MATCH_FRAMES, N_FIGHTERS, 4)
+
+
+def window_bytes(boxes_px, padding=30):
+    """Algorithmic HBM bytes of the preprocess kernel: clipped raw window read once."""
+    cx, cy, cw, ch = [boxes_px[..., i].astype(np.int64) for i in range(4)]
+    sd = np.maximum(cw, ch)
+    half = sd // 2
+    y0 = np.maximum(cy - half - padding, 0); y1 = np.minimum(cy + half + padding, H)
+    x0 = np.maximum(cx - half - padding, 0); x1 = np.minimum(cx + half + padding, W)
+    return 3 * np.maximum(y1 - y0, 0) * np.maximum(x1 - x0, 0)
+
+
+# ------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reference(sample_frames: int, seed: int, threads: int | None = None, as_shipped: bool = False):
+    """Oracle port on the host cores over `sample_frames` frames of the bench workload.
+    Returns (frames_per_s, seconds, cores)."""
+    import torch
+
+    from oracle import ref_path
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.fighter import yolo_pixels_batch
+    from workloads import synthetic, weights
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    try:
+        import cv2
+
+        cv2.setNumThreads(cores)
+    except Exception:
+        pass
+    boxes = match_boxes(seed)[:sample_frames]
+    frames = synthetic.synth_frames(np.arange(sample_frames), yolo_pixels_batch(boxes, W, H), device="cpu").numpy()
+    model = ref_path.RefCNNActionDetector(ACTIONS, 7).eval()
+    model.load_state_dict(weights.calibrated_state_dict(0))
+    ref_path.classify_clip(frames[:2], boxes[:2], model)  # warm-up (thread pools, oneDNN primitives)
+    t0 = time.perf_counter()
+    ref_path.classify_clip(frames, boxes, model, as_shipped=as_shipped)
+    dt = time.perf_counter() - t0
+    return sample_frames / dt, dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 16
+    vals = []
+    for _ in range(args.warmup):
+        pass  # the port warms itself up inside cpu_reference
+    for _ in range(max(1, min(args.steps, 3))):
+        fps, dt, cores = cpu_reference(per_step, seed=2024)
+        vals.append((fps, dt))
+    fps = float(np.mean([v[0] for v in vals]))
+    ms = float(np.mean([v[1] for v in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3-minute synthetic 1080p match, 2 fighters; each step = a 16-frame sample (32 crops, 32 windows)",
+                   "batch_frames": per_step, "fighters": N_FIGHTERS, "resolution": "1920x1080"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} frames/step x {len(vals)} steps; oracle/ref_path.py (cv2+Pillow crops, torch CPU ResNet-18 once per crop)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from playaid_core_b200 import _lib
+    from playaid_core_b200.action_detector import ActionDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.fighter import yolo_pixels_batch
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from workloads import synthetic, weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+
+    # ---- workload: each rank owns a different synthetic match (video-level sharding)
+    boxes = match_boxes(seed=2024 + rank)
+    px = yolo_pixels_batch(boxes, W, H)
+    resident = []
+    for b in range(N_RESIDENT):
+        sl = slice(b * BATCH_FRAMES, (b + 1) * BATCH_FRAMES)
+        resident.append(synthetic.synth_frames(np.arange(sl.start, sl.stop), px[sl], device=dev, seed=1234 + rank))
+    model = CNNActionDetector(ACTIONS, sequence_length=7, precision=args.precision, device=dev).eval()
+    model.load_state_dict(weights.calibrated_state_dict(0))
+    det = ActionDetector(model)
+    ctx = _lib.Context.get(dev)
+    n_chunks = MATCH_FRAMES // BATCH_FRAMES
+    gathered = torch.empty((world, BATCH_FRAMES * N_FIGHTERS), dtype=torch.int32, device=dev) if world > 1 else None
+
+    state = {"stream": det.stream(boxes, H, W), "chunk": 0}
+
+    def step(frames_dev):
+        """One batch through the public API: crops -> features -> head for the frames that became final."""
+        if state["chunk"] == n_chunks:
+            state["stream"], state["chunk"] = det.stream(boxes, H, W), 0
+        st = state["stream"]
+        a, b = st.push(frames_dev)
+        state["chunk"] += 1
+        if world > 1 and b > a:  # label gather over NVLink (the path's only collective)
+            lab = torch.full((BATCH_FRAMES * N_FIGHTERS,), -1, dtype=torch.int32, device=dev)
+            lab[: (b - a) * N_FIGHTERS] = st.label[a:b].reshape(-1)
+            dist.all_gather_into_tensor(gathered.view(-1), lab)
+        return st, a, b
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for i in range(Wm):
+        step(resident[i % N_RESIDENT])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(resident[(Wm + i) % N_RESIDENT])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * BATCH_FRAMES / (ms_max / 1e3)
+
+    # ---- end to end from pinned host memory (H2D of the frames + D2H of labels/probabilities per step)
+    host = [torch.empty((BATCH_FRAMES, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for hb, src in zip(host, resident):
+        hb.copy_(src)
+    stage = torch.empty((BATCH_FRAMES, H, W, 3), dtype=torch.uint8, device=dev)
+    out_host = torch.empty((BATCH_FRAMES * N_FIGHTERS, 2), dtype=torch.float32).pin_memory()
+    h2d = BATCH_FRAMES * H * W * 3
+    d2h = BATCH_FRAMES * N_FIGHTERS * 8
+
+    def e2e_step(i):
+        stage.copy_(host[i % 2], non_blocking=True)
+        st, a, b = step(stage)
+        if b > a:
+            n = (b - a) * N_FIGHTERS
+            out_host[:n, 0].copy_(st.label[a:b].reshape(-1).float(), non_blocking=True)
+            out_host[:n, 1].copy_(st.prob[a:b].reshape(-1), non_blocking=True)
+
+    Ke = max(2, min(K, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(Ke):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * Ke * BATCH_FRAMES / (float(t.item()) / 1e3)
+
+    # ---- per-kernel CUDA-event timing for the roofline (separate pass, not part of `value`)
+    roofline = None
+    kernels = {}
+    if rank == 0:
+        state["stream"], state["chunk"] = det.stream(boxes, H, W), 0
+        step(resident[0])
+        torch.cuda.synchronize()
+        Kp = max(2, min(K, 8))
+        ctx.profile_begin()
+        c0 = state["chunk"]
+        for i in range(Kp):
+            step(resident[(1 + i) % N_RESIDENT])
+        prof = ctx.profile_end()
+        pk = peaks()
+        total_ms = sum(v[1] for v in prof.values())
+        # algorithmic work per step
+        crops_per_step = BATCH_FRAMES * N_FIGHTERS
+        wb = window_bytes(px[c0 * BATCH_FRAMES : (c0 + Kp) * BATCH_FRAMES]).sum() / Kp
+        pre_bytes = float(wb + crops_per_step * 128 * 128 * 3 * 2)  # window read + bf16 output
+        conv_ms = sum(v[1] for k, v in prof.items() if k.startswith("conv")) / Kp
+        for name, (n, tms) in prof.items():
+            kernels[name] = {"launches_per_step": n / Kp, "ms_per_step": tms / Kp, "share": tms / total_ms}
+        pre_ms = (prof.get("preprocess", (0, 0.0))[1] + prof.get("preprocess_large_windows", (0, 0.0))[1]) / Kp
+        cls_flops = crops_per_step * FLOP_PER_CROP
+        tensor_achieved = cls_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+        hbm_achieved = pre_bytes / (pre_ms / 1e3) / 1e9 if pre_ms > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "kernel": "conv_gemm_kernel + conv1_kernel (ResNet-18 implicit GEMMs, all layers)",
+            "achieved": tensor_achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": tensor_achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+            "algorithmic_flop_per_step": cls_flops, "ms_per_step": conv_ms, "share_of_step": conv_ms / (total_ms / Kp),
+        }
+        roofline_pre = {
+            "bound": "hbm", "kernel": "preprocess_kernel", "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": hbm_achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+            "algorithmic_bytes_per_step": pre_bytes, "ms_per_step": pre_ms, "share_of_step": pre_ms / (total_ms / Kp),
+        }
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            fps, dt, cores = cpu_reference(24, seed=2024)
+            fps_s, dt_s, _ = cpu_reference(4, seed=2024, as_shipped=True)
+            cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first 24 frames (48 crops, 48 windows) of the same match in {dt:.1f} s, features once per crop; "
+                             f"as shipped (7x ResNet per window, batch 1): {fps_s:.2f} frames/s on 4 frames"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "bf16x2": "bf16x2 (split bf16 hi+lo, fp32-parity mode)", "bf16x3": "bf16x3"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "single 1080p 60fps 3-minute synthetic match, 2 fighters, batch 256 frames (BASELINE configs[1]); "
+                                   "one match per GPU", "batch_frames": BATCH_FRAMES, "fighters": N_FIGHTERS, "resolution": "1920x1080",
+                       "crop": "square_crop(128, padding=30) exact Pillow-bicubic + INTER_AREA chain", "window": "7 frames, delta 3",
+                       "weights": "reference architecture, seeded calibrated random init", "precision": args.precision,
+                       "l2": f"inputs larger than L2: {N_RESIDENT} resident batches of 1.59 GB cycled", "parallelism": f"dp{world}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_preprocess": roofline_pre, "kernels": kernels,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x2", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,11 @@ int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, int hin,
 int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, const float* w_host, const float* scale_host,
             const float* shift_host, void* out_hi, void* out_lo, int split_w, void* stream);
 
+/* Per-kernel device timing: between begin and end every launch of this context is bracketed by a
+ * CUDA event pair on its stream; end writes "name<TAB>launches<TAB>total_ms" lines into buf (host). */
+int pa_profile_begin(pa_ctx* ctx);
+int pa_profile_end(pa_ctx* ctx, char* buf, size_t buflen);
+
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t pa_launch_count(pa_ctx* ctx);
 

@@ -20,6 +20,7 @@ EXPORTS = [
     "pa_abi_version", "pa_status_string", "pa_last_error", "pa_ctx_create", "pa_ctx_destroy", "pa_preprocess",
     "pa_model_create", "pa_model_destroy", "pa_model_set_tensor", "pa_model_finalize", "pa_model_precision",
     "pa_model_workspace_bytes", "pa_features", "pa_crop_elems", "pa_head", "pa_launch_count", "pa_conv2d", "pa_stem",
+    "pa_profile_begin", "pa_profile_end",
 ]
 
 
@@ -65,6 +66,8 @@ def load() -> ctypes.CDLL:
     fp = c.POINTER(c.c_float)
     lib.pa_conv2d.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.pa_stem.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp]
+    lib.pa_profile_begin.argtypes = [vp]
+    lib.pa_profile_end.argtypes = [vp, c.c_char_p, sz]
     lib.pa_launch_count.restype = i64
     lib.pa_launch_count.argtypes = [vp]
     for name in EXPORTS:
@@ -114,6 +117,19 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.pa_launch_count(self.handle))
+
+    def profile_begin(self) -> None:
+        check(self.lib.pa_profile_begin(self.handle), self.handle, "pa_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{kernel name: (launches, total_ms)} in first-launch order."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(self.lib.pa_profile_end(self.handle, buf, len(buf)), self.handle, "pa_profile_end")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name] = (int(n), float(ms))
+        return out
 
 
 def current_stream_ptr(device=None) -> ctypes.c_void_p:

@@ -29,12 +29,17 @@ from .preprocess import crop_records, preprocess_crops
 
 
 class MatchStream:
-    """Streaming state for one match: feature table + how far crops / labels have progressed."""
+    """Streaming state for one match: crop records and window tables (device-resident, built once from
+    the whole log), the feature table, and how far crops / labels have progressed."""
 
-    def __init__(self, det: "ActionDetector", total_frames: int, n_fighters: int, H: int, W: int):
-        self.det, self.N, self.F, self.H, self.W = det, int(total_frames), int(n_fighters), int(H), int(W)
+    def __init__(self, det: "ActionDetector", boxes: np.ndarray, H: int, W: int):
+        self.det, self.H, self.W = det, int(H), int(W)
+        self.N, self.F = int(boxes.shape[0]), int(boxes.shape[1])
+        self.boxes = boxes
         dev = det.model._device
-        A = det.model.num_actions
+        A, S = det.model.num_actions, det.num_frames_per_sample
+        rec = crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(self.N), self.F), self.W, self.H)
+        self.rec = torch.from_numpy(rec).to(dev)
         self.feat = torch.zeros((self.N * self.F, 1000), dtype=torch.float32, device=dev)
         self.logp = torch.empty((self.N, self.F, A), dtype=torch.float32, device=dev)
         self.label = torch.full((self.N, self.F), -1, dtype=torch.int32, device=dev)
@@ -42,45 +47,43 @@ class MatchStream:
         self.status = torch.zeros((self.N, self.F), dtype=torch.int32, device=dev)
         self.pushed = 0   # frames whose features are in the table
         self.labeled = 0  # frames whose windows have been classified
-        # all window indices of the match, as frame numbers (host) -- dataset_utils.py:109-138
-        self.win_frames = window_index_table(
-            np.arange(det.min_frame, self.N), det.num_frames_per_sample, det.frame_delta, max_frames=self.N,
-            min_frame=det.min_frame,
-        )
-        mid = det.num_frames_per_sample // 2
+        # window indices of every frame, as frame numbers (host) -- dataset_utils.py:109-138
+        self.win_frames = window_index_table(np.arange(det.min_frame, self.N), S, det.frame_delta, max_frames=self.N,
+                                             min_frame=det.min_frame)
+        # ... and as feature-table rows (device): row = frame * F + fighter
+        idx = self.win_frames[:, None, :].astype(np.int64) * self.F + np.arange(self.F)[None, :, None]
+        self.win_rows = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(dev)  # [N-min, F, S]
+        mid = S // 2
         self.reach = det.frame_delta * mid * mid
 
-    def push(self, frames: torch.Tensor, boxes: np.ndarray) -> tuple[int, int]:
-        """frames uint8 CUDA [n,H,W,3] for match frames [pushed, pushed+n); boxes float64 [n,F,4].
-        Returns the [a, b) range of frames labelled by this call."""
+    def push(self, frames: torch.Tensor) -> tuple[int, int]:
+        """frames uint8 CUDA [n,H,W,3]: match frames [pushed, pushed+n). Returns the [a, b) range of
+        frames labelled by this call (labels trail by the window reach until the match ends)."""
         det = self.det
         n = int(frames.shape[0])
         f0 = self.pushed
-        assert boxes.shape[:2] == (n, self.F) and f0 + n <= self.N
-        rec = crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(n), self.F), self.W, self.H)
-        rec_d = torch.from_numpy(rec).to(frames.device, non_blocking=True)
+        assert f0 + n <= self.N
+        rec = self.rec[f0 * self.F : (f0 + n) * self.F].clone()
+        rec[:, 0] -= f0  # frame index relative to this chunk
         crops, status = preprocess_crops(
-            frames, rec_d, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
+            frames, rec, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
             dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4, out=det._crop_buffer(n * self.F),
+            status=self.status[f0 : f0 + n].view(-1),
         )
-        self.status[f0 : f0 + n] = status.view(n, self.F)
         det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
         self.pushed = f0 + n
         return self._label_ready()
 
     def _label_ready(self) -> tuple[int, int]:
         det = self.det
-        a = self.labeled
+        a = max(self.labeled, det.min_frame)
         b = self.N if self.pushed == self.N else max(a, self.pushed - self.reach)
-        a = max(a, det.min_frame)
         if b <= a:
             return (a, a)
-        # feature rows needed by windows centred on [a, b)
-        wf = self.win_frames[a - det.min_frame : b - det.min_frame]  # [nb, S] frame numbers
-        lo, hi = int(wf.min()), int(wf.max()) + 1
-        idx = (wf[:, None, :] - lo) * self.F + np.arange(self.F)[None, :, None]  # [nb, F, S] rows rel. to lo*F
-        idx_d = torch.from_numpy(np.ascontiguousarray(idx.reshape(-1, wf.shape[1]).astype(np.int32))).to(self.feat.device)
-        logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx_d)
+        wf = self.win_frames[a - det.min_frame : b - det.min_frame]
+        lo, hi = int(wf.min()), int(wf.max()) + 1  # feature rows the windows centred on [a, b) touch
+        idx = (self.win_rows[a - det.min_frame : b - det.min_frame] - lo * self.F).view(-1, wf.shape[1]).contiguous()
+        logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx)
         self.logp[a:b] = logp.view(b - a, self.F, -1)
         self.label[a:b] = label.view(b - a, self.F)
         self.prob[a:b] = prob.view(b - a, self.F)
@@ -117,16 +120,17 @@ class ActionDetector:
             self._crops = torch.empty(shape, dtype=torch.bfloat16, device=self.model._device)
         return self._crops
 
-    def stream(self, total_frames: int, n_fighters: int, H: int, W: int) -> MatchStream:
-        return MatchStream(self, total_frames, n_fighters, H, W)
+    def stream(self, boxes: np.ndarray, H: int, W: int) -> MatchStream:
+        """boxes float64 [N,F,4]: every (frame, fighter) box of the match (from the ult_logger log)."""
+        return MatchStream(self, boxes, H, W)
 
     def classify_clip(self, frames: torch.Tensor, boxes: np.ndarray, chunk: int = 256) -> dict:
         """frames uint8 CUDA [N,H,W,3] (BGR, as decoded by cv2), boxes float64 [N,F,4] normalised.
         Returns device tensors: label [N,F] int32, logp [N,F,A], prob [N,F], status [N,F]."""
         N, H, W, _ = frames.shape
-        st = self.stream(N, boxes.shape[1], H, W)
+        st = self.stream(boxes[:N], H, W)
         for s in range(0, N, chunk):
-            st.push(frames[s : s + chunk], boxes[s : s + chunk])
+            st.push(frames[s : s + chunk])
         return {"label": st.label, "logp": st.logp, "prob": st.prob, "status": st.status}
 
     def classify_timeline(self, frames: torch.Tensor, timeline, chunk: int = 256) -> dict:

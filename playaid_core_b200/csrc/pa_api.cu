@@ -19,7 +19,64 @@ struct pa_ctx {
     int64_t launches = 0;
     std::string last_error;
     decltype(&cuTensorMapEncodeTiled) encode_tiled = nullptr;
+    int32_t* pp_status = nullptr;  // scratch per-crop status when the caller passes none
+    int pp_status_cap = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Span { std::string name; cudaEvent_t e0, e1; };
+    std::vector<Span> spans;
 };
+
+static int cuda_fail(pa_ctx* ctx, cudaError_t e, const char* what);
+
+// RAII span: records an event pair around one launch when profiling is on
+struct ProfSpan {
+    pa_ctx* ctx; cudaStream_t st; int idx = -1;
+    ProfSpan(pa_ctx* c, const std::string& name, cudaStream_t s) : ctx(c), st(s) {
+        if (!ctx || !ctx->profiling) return;
+        pa_ctx::Span sp; sp.name = name;
+        cudaEventCreate(&sp.e0); cudaEventCreate(&sp.e1);
+        cudaEventRecord(sp.e0, st);
+        ctx->spans.push_back(sp);
+        idx = (int)ctx->spans.size() - 1;
+    }
+    ~ProfSpan() { if (idx >= 0) cudaEventRecord(ctx->spans[idx].e1, st); }
+};
+
+extern "C" int pa_profile_begin(pa_ctx* ctx) {
+    if (!ctx) return PA_ERR_INVALID_ARG;
+    for (auto& s : ctx->spans) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+    ctx->spans.clear();
+    ctx->profiling = true;
+    return PA_OK;
+}
+
+// Stops profiling, synchronises the recorded events and writes "name\tlaunches\ttotal_ms\n" lines.
+extern "C" int pa_profile_end(pa_ctx* ctx, char* buf, size_t buflen) {
+    if (!ctx || !buf || buflen == 0) return PA_ERR_INVALID_ARG;
+    ctx->profiling = false;
+    std::map<std::string, std::pair<int, double>> acc;
+    std::vector<std::string> order;
+    for (auto& s : ctx->spans) {
+        if (cudaEventSynchronize(s.e1) != cudaSuccess) return cuda_fail(ctx, cudaGetLastError(), "profile sync");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.e0, s.e1);
+        if (!acc.count(s.name)) order.push_back(s.name);
+        acc[s.name].first += 1;
+        acc[s.name].second += ms;
+        cudaEventDestroy(s.e0); cudaEventDestroy(s.e1);
+    }
+    ctx->spans.clear();
+    std::string out;
+    for (auto& n : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", n.c_str(), acc[n].first, acc[n].second);
+        out += line;
+    }
+    if (out.size() + 1 > buflen) return PA_ERR_WORKSPACE;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return PA_OK;
+}
 
 static int cuda_fail(pa_ctx* ctx, cudaError_t e, const char* what) {
     if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -77,6 +134,7 @@ extern "C" int pa_ctx_create(int device, pa_ctx** out) {
 }
 
 extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
+    if (ctx && ctx->pp_status) cudaFree(ctx->pp_status);
     delete ctx;
     return PA_OK;
 }
@@ -107,11 +165,34 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     p.outp = out; p.out_dtype = out_dtype; p.out_layout = out_layout;
     const int ch = (out_layout == PA_LAYOUT_NHWC4) ? 4 : 3;
     p.plane_elems = (int64_t)n_crops * out_size * out_size * ch;
+    if (!status) {
+        if (ctx->pp_status_cap < n_crops) {
+            if (ctx->pp_status) cudaFree(ctx->pp_status);
+            ctx->pp_status = nullptr; ctx->pp_status_cap = 0;
+            PA_CUDA(ctx, cudaMalloc((void**)&ctx->pp_status, (size_t)n_crops * sizeof(int32_t)));
+            ctx->pp_status_cap = n_crops;
+        }
+        status = ctx->pp_status;
+    }
     p.status = status;
+    // pass 1: 100 KB of shared memory per CTA (2 CTAs / SM) covers windows up to ~600 px;
+    // pass 2: the few crops that did not fit are redone with the whole 227 KB carve-out.
     p.smem_bytes = 100 * 1024;
-    int rc = launch_preprocess(p, (cudaStream_t)stream);
+    p.first_pass_smem = 0;
+    int rc;
+    {
+        ProfSpan sp(ctx, "preprocess", (cudaStream_t)stream);
+        rc = launch_preprocess(p, (cudaStream_t)stream);
+    }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
-    ctx->launches += 1;
+    p.smem_bytes = 227 * 1024;
+    p.first_pass_smem = 100 * 1024;
+    {
+        ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);
+        rc = launch_preprocess(p, (cudaStream_t)stream);
+    }
+    if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch (large windows)");
+    ctx->launches += 2;
     return PA_OK;
 }
 
@@ -137,6 +218,7 @@ struct ConvLayer {
 };
 
 struct PlanOp {
+    char name[64];
     int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool
     Conv1Args c1;
     ConvMaps maps;
@@ -450,6 +532,13 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     pa_ctx* ctx = m->ctx;
     memset(&op.maps, 0, sizeof(op.maps));
     op.kind = 2;
+    {
+        std::string nm = L.w_key.empty() ? std::string("temporal_proj") : L.w_key;
+        const std::string pre = "cnn2d.", suf = ".weight";
+        if (nm.rfind(pre, 0) == 0) nm = nm.substr(pre.size());
+        if (nm.size() > suf.size() && nm.compare(nm.size() - suf.size(), suf.size(), suf) == 0) nm = nm.substr(0, nm.size() - suf.size());
+        snprintf(op.name, sizeof(op.name), "conv_gemm:%s", nm.c_str());
+    }
     const int n_a = in.lo ? 2 : 1, n_b = L.w_lo ? 2 : 1;
     const int hout = L.hin / L.stride;
     int wt, ht, nt;
@@ -516,6 +605,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
     {
         PlanOp op; memset(&op, 0, sizeof(op));
         op.kind = 0;
+        snprintf(op.name, sizeof(op.name), "conv1_stem");
         op.c1.in_hi = (const bf16*)crops;
         op.c1.in_lo = split ? (const bf16*)crops + (size_t)n * 128 * 128 * 4 : nullptr;
         op.c1.w_hi = m->stem_w_hi; op.c1.w_lo = m->stem_w_lo;
@@ -527,6 +617,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
     {
         PlanOp op; memset(&op, 0, sizeof(op));
         op.kind = 1;
+        snprintf(op.name, sizeof(op.name), "maxpool");
         op.pin_hi = big.hi; op.pin_lo = big.lo; op.pout_hi = sm[0].hi; op.pout_lo = sm[0].lo;
         op.pn = n; op.ph = 64; op.pw = 64; op.pc = 64;
         m->plan.push_back(op);
@@ -557,6 +648,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
     {
         PlanOp op; memset(&op, 0, sizeof(op));
         op.kind = 3;
+        snprintf(op.name, sizeof(op.name), "avgpool");
         op.pin_hi = sm[x].hi; op.pin_lo = sm[x].lo; op.pout_hi = pooled.hi; op.pout_lo = pooled.lo;
         op.pn = n; op.ph = 16; op.pc = 512;
         m->plan.push_back(op);
@@ -583,6 +675,7 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
     }
     for (const PlanOp& op : m->plan) {
         int rc = PA_OK;
+        ProfSpan sp(ctx, op.name, st);
         switch (op.kind) {
             case 0: rc = launch_conv1(op.c1, ctx->num_sms, st); break;
             case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, st); break;
@@ -614,16 +707,26 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
         m->head_gemm.args.scale = nullptr; m->head_gemm.args.shift = nullptr;
         m->hplan_n = n_feat; m->hplan_feat = feat; m->hplan_ws = workspace;
     }
-    int rc = launch_split_f32(feat, fb.hi, fb.lo, (int64_t)n_feat * 1000, st);
+    int rc;
+    {
+        ProfSpan sp(ctx, "feat_to_bf16", st);
+        rc = launch_split_f32(feat, fb.hi, fb.lo, (int64_t)n_feat * 1000, st);
+    }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "split launch");
     const PlanOp& g = m->head_gemm;
-    rc = launch_conv_gemm(g.maps, g.args, g.block_n, g.n_a, g.n_b, ctx->num_sms, st);
+    {
+        ProfSpan sp(ctx, g.name, st);
+        rc = launch_conv_gemm(g.maps, g.args, g.block_n, g.n_a, g.n_b, ctx->num_sms, st);
+    }
     if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "projection launch") : rc;
     HeadArgs h;
     h.proj = proj; h.win_idx = win_idx; h.n_win = n_win; h.n_feat = n_feat; h.seq = m->seq; h.n_actions = m->n_actions;
     h.b1d = m->b1d; h.w1t = m->w1t; h.b1 = m->b1; h.w2t = m->w2t; h.b2 = m->b2;
     h.logp = logp; h.label = label; h.conf = conf;
-    rc = launch_head(h, st);
+    {
+        ProfSpan sp(ctx, "head_mlp_softmax", st);
+        rc = launch_head(h, st);
+    }
     if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "head launch") : rc;
     ctx->launches += 3;
     return PA_OK;

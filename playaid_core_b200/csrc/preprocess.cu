@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
     __syncthreads();
     const int F0 = (int)((int64_t)part * out / PP_SPLIT), F1 = (int)((int64_t)(part + 1) * out / PP_SPLIT);
     if (g.status != PA_CROP_OK) {
+        if (p.first_pass_smem > 0) return;  // reported by the first pass
         if (part == 0 && tid == 0 && p.status) p.status[crop] = g.status;
         zero_rows(p, crop, F0, F1);
         return;
@@ -380,30 +381,35 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
     const int tp = align16(nw3), sp = align16(sd3);
     const int ycap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2;
     if (tid == 0) {
-        int B = F1 - F0;
-        for (; B >= 1; B = (B > 1 ? (B + 1) / 2 : 0)) {
-            // upper bounds of rows needed for B final rows
-            int ns, nt;
-            if (g.regime == REG_COPY) ns = B;
-            else if (g.regime == REG_FAST) ns = B * g.isy;
-            else if (g.regime == REG_GENERAL) ns = (int)ceil(B * g.scale_y) + 2;
-            else ns = (int)ceil(B * g.scale_y) + 2;
-            if (ns > sd) ns = sd;
-            nt = ns;
-            if (g.vact) nt = (int)ceil(ns * g.v_scale) + 2 * (int)ceil(g.v_sup) + 2;
-            if (nt > rh) nt = rh;
-            int need = off + B * (2 + ycap * 2) * 4 + 64;            // y tables
-            if (g.vact) need += ns * (2 + g.v_ks) * 4;                // V tables
-            need += nt * rawp;                                        // RAW
-            if (g.hact) need += nt * tp;                              // T
-            if (g.pad1) need += ns * sp;                              // S
-            if (need <= p.smem_bytes) break;
-            if (B == 1) { B = 0; break; }
-        }
-        s_band_rows = B;
+        // largest band (final rows per pass) whose staging fits in `limit` bytes of shared memory
+        auto fit = [&](int limit) {
+            int B = F1 - F0;
+            for (; B >= 1; B = (B > 1 ? (B + 1) / 2 : 0)) {
+                int ns, nt;  // upper bounds of canvas / raw rows needed for B final rows
+                if (g.regime == REG_COPY) ns = B;
+                else if (g.regime == REG_FAST) ns = B * g.isy;
+                else ns = (int)ceil(B * g.scale_y) + 2;
+                if (ns > sd) ns = sd;
+                nt = ns;
+                if (g.vact) nt = (int)ceil(ns * g.v_scale) + 2 * (int)ceil(g.v_sup) + 2;
+                if (nt > rh) nt = rh;
+                int need = off + B * (2 + ycap * 2) * 4 + 64;  // y tables
+                if (g.vact) need += ns * (2 + g.v_ks) * 4;      // V tables
+                need += nt * rawp;                              // RAW
+                if (g.hact) need += nt * tp;                    // T
+                if (g.pad1) need += ns * sp;                    // S
+                if (need <= limit) return B;
+                if (B == 1) break;
+            }
+            return 0;
+        };
+        // second pass (whole 227 KB carve-out): only crops the first pass could not stage
+        if (p.first_pass_smem > 0 && fit(p.first_pass_smem) > 0) s_band_rows = -1;
+        else s_band_rows = fit(p.smem_bytes);
     }
     __syncthreads();
     const int B = s_band_rows;
+    if (B < 0) return;  // already produced by the first pass
     if (B == 0) {  // does not fit in shared memory even one output row at a time
         if (part == 0 && tid == 0 && p.status) p.status[crop] = PA_CROP_TOO_LARGE;
         zero_rows(p, crop, F0, F1);
@@ -678,7 +684,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
 int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return PA_ERR_CUDA;
         attr_set = true;
     }

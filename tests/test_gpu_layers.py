@@ -159,8 +159,9 @@ def test_stem_vs_torch(env, split):
     lo = (x4 - hi.float()).to(torch.bfloat16) if split else None
     out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
     out_lo = torch.zeros_like(out_hi) if split else None
-    rc = ctx.lib.pa_stem(ctx.handle, _ptr(hi), _ptr(lo), N, w.cpu().contiguous().data_ptr(), scale.cpu().data_ptr(),
-                         shift.cpu().data_ptr(), _ptr(out_hi), _ptr(out_lo), 0, _lib.current_stream_ptr())
+    wc, sc, sh = w.cpu().contiguous(), scale.cpu().contiguous(), shift.cpu().contiguous()  # keep alive across the call
+    rc = ctx.lib.pa_stem(ctx.handle, _ptr(hi), _ptr(lo), N, wc.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(out_hi),
+                         _ptr(out_lo), 0, _lib.current_stream_ptr())
     _lib.check(rc, ctx.handle, "pa_stem")
     torch.cuda.synchronize()
     y = (out_hi.float() + (out_lo.float() if split else 0)).permute(0, 3, 1, 2)

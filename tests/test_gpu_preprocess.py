@@ -103,7 +103,9 @@ def test_output_formats(torch_cuda, golden_frames):
     boxes = np.stack([rng.uniform(0.1, 0.9, 16), rng.uniform(0.1, 0.9, 16), rng.uniform(0.05, 0.3, 16), rng.uniform(0.05, 0.4, 16)], 1)
     rec = torch.from_numpy(crop_records(boxes, rng.integers(0, 3, 16), 1920, 1080)).cuda()
     u8, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
-    want = (u8.flip(-1).permute(0, 3, 1, 2).float() / 255.0)  # cvtColor(BGR2RGB) + permute + /255
+    # cvtColor(BGR2RGB) + permute + .float()/255.0 evaluated on the CPU like the reference (torch's CUDA
+    # scalar division multiplies by a reciprocal and differs in the last bit for 126 of 256 values)
+    want = (u8.cpu().flip(-1).permute(0, 3, 1, 2).float() / 255.0).cuda()
     f32, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F32, layout=_lib.LAYOUT_NCHW)
     assert torch.equal(f32, want)
     nhwc, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F32, layout=_lib.LAYOUT_NHWC)
@@ -118,7 +120,7 @@ def test_output_formats(torch_cuda, golden_frames):
     ms, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, mean=mean, std=std, dtype=_lib.DTYPE_F32, layout=_lib.LAYOUT_NCHW)
     m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
     s = torch.tensor(std, device="cuda").view(1, 3, 1, 1)
-    assert torch.equal(ms, (want - m) / s)
+    assert torch.equal(ms.cpu(), (want.cpu() - m.cpu()) / s.cpu())
     sw_u8, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NCHW)
     assert torch.equal(sw_u8, u8.flip(-1).permute(0, 3, 1, 2))
 
