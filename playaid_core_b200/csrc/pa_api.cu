@@ -185,7 +185,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         rc = launch_preprocess(p, (cudaStream_t)stream);
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
-    p.smem_bytes = 227 * 1024;
+    p.smem_bytes = 224 * 1024;
     p.first_pass_smem = 100 * 1024;
     {
         ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);

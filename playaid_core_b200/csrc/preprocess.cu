@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
 int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return PA_ERR_CUDA;
         attr_set = true;
     }
