@@ -331,7 +331,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"bf16": "bf16", "bf16x2": "bf16x2 (split bf16 hi+lo, fp32-parity mode)", "bf16x3": "bf16x3"}[args.precision],
+            "dtype": args.precision,
             "data": "synthetic",
             "config": {"workload": "single 1080p 60fps 3-minute synthetic match, 2 fighters, batch 256 frames (BASELINE configs[1]); "
                                    "one match per GPU", "batch_frames": BATCH_FRAMES, "fighters": N_FIGHTERS, "resolution": "1920x1080",
@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x2", "bf16x3"])
+    ap.add_argument("--precision", default="f16", choices=["bf16", "bf16x2", "bf16x3", "f16", "f16x2", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -43,6 +43,8 @@ extern "C" {
 #define PA_DTYPE_BF16 1
 #define PA_DTYPE_F32 2
 #define PA_DTYPE_BF16X2 3 /* bf16 hi plane followed by a bf16 lo (rounding residual) plane */
+#define PA_DTYPE_F16 4    /* IEEE half */
+#define PA_DTYPE_F16X2 5  /* half hi plane followed by a half lo (rounding residual) plane */
 #define PA_LAYOUT_NHWC 0
 #define PA_LAYOUT_NCHW 1
 #define PA_LAYOUT_NHWC4 2 /* 4 channels per pixel, channel 3 == 0: the conv1-ready layout */
@@ -52,6 +54,11 @@ extern "C" {
 #define PA_PREC_BF16X2 1 /* activations split hi+lo bf16, weights bf16: 2 MMAs; exact to ~1e-5
                             when the weights are bf16-representable                              */
 #define PA_PREC_BF16X3 2 /* weights split as well: 3 MMAs, for arbitrary fp32 checkpoints        */
+#define PA_PREC_F16 3    /* IEEE-half operands (11-bit significand), fp32 accumulate: same tensor
+                            rate as bf16, 8x smaller rounding error; activations must stay < 65504 */
+#define PA_PREC_F16X2 4  /* activations split hi+lo half (~22 bits), weights half: the fp32-parity
+                            mode (1e-4) when the weights are half-representable                   */
+#define PA_PREC_F16X3 5  /* weights split as well: fp32-parity for arbitrary fp32 checkpoints       */
 
 #define PA_BOX_STRIDE 8 /* int32 per crop record */
 /* crop record layout: {frame_index, cx, cy, cw, ch, reserved, reserved, reserved}; (cx,cy,cw,ch)
@@ -136,7 +143,8 @@ int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, 
  * the output), and the 7x7/s2 stem on NHWC4 crops. Weights / scale / shift are host fp32 in PyTorch
  * layout; y = conv(x, w) * scale + shift (+ residual) (ReLU). These are the building blocks
  * pa_features sequences; exposed for layer-level parity tests against torch.nn.functional.conv2d.
- * in_lo / out_lo / res_lo may be NULL (plain bf16); split_w != 0 also splits the weights (3 MMAs).
+ * in_lo / out_lo / res_lo may be NULL (no split). split_w is a flag word: bit 0 = split the weights
+ * too (3 MMAs), bit 1 = the 16-bit planes are IEEE half instead of bfloat16.
  */
 int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, int hin, int cin, const float* w_host, int cout,
               int k, int stride, int pad, const float* scale_host, const float* shift_host, const void* res_hi,

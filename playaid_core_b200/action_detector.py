@@ -116,8 +116,8 @@ class ActionDetector:
     def _crop_buffer(self, n: int) -> torch.Tensor:
         planes = 2 if self.model.split else 1
         shape = (planes, n, self.output_size, self.output_size, 4) if planes == 2 else (n, self.output_size, self.output_size, 4)
-        if self._crops is None or tuple(self._crops.shape) != shape:
-            self._crops = torch.empty(shape, dtype=torch.bfloat16, device=self.model._device)
+        if self._crops is None or tuple(self._crops.shape) != shape or self._crops.dtype != self.model.act_dtype:
+            self._crops = torch.empty(shape, dtype=self.model.act_dtype, device=self.model._device)
         return self._crops
 
     def stream(self, boxes: np.ndarray, H: int, W: int) -> MatchStream:

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const Conv1Args a)
     } else if (warp == 8) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, C1_COUT);
+            const uint32_t idesc = a.f16 ? umma_idesc_f16(128, C1_COUT) : umma_idesc_bf16(128, C1_COUT);
             const uint32_t sb0 = smem_u32(sB);
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
@@ -151,9 +151,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const Conv1Args a)
                 for (int i = 0; i < 8; i++) {
                     float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
                     float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
-                    const bf16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    l[i] = pack_bf16x2(x0 - __bfloat162float(h0), x1 - __bfloat162float(h1));
+                    if (a.f16) split2<true>(x0, x1, h[i], l[i]);
+                    else split2<false>(x0, x1, h[i], l[i]);
                 }
                 uint4* op = (uint4*)(a.out_hi + o + c0);
                 op[0] = make_uint4(h[0], h[1], h[2], h[3]);

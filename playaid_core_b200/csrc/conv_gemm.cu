@@ -39,6 +39,123 @@ int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
     return s;
 }
 
+// Epilogue of one CTA: TMEM accumulator -> fp32 scale/shift (folded BN or bias) -> (+ residual) -> (ReLU)
+// -> 16-bit hi (+ lo) planes or fp32. One thread per accumulator row (= output pixel); its channels are
+// contiguous in NHWC, so every access is a 32-byte run. The residual of the next 16-column chunk is
+// prefetched while the current chunk is processed.
+template <int BLOCK_N, bool F16>
+__device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                         int warp, int lane, int total_tiles) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const bool has_res = args.res_hi != nullptr;
+    const bool has_res_lo = args.res_lo != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        const int64_t row = (int64_t)mt * CG_BLOCK_M + r;
+        const bool row_ok = row < args.m_total;
+        const int n_base = nt * BLOCK_N;
+        const int64_t o_base = row * args.cout + n_base;
+        uint4 rh0, rh1, rl0, rl1;  // residual of the current chunk
+        rh0 = rh1 = rl0 = rl1 = make_uint4(0, 0, 0, 0);
+        auto load_res = [&](int c0, uint4& a0, uint4& a1, uint4& b0, uint4& b1) {
+            if (has_res && row_ok && n_base + c0 + 16 <= args.cout) {
+                const uint4* rp = (const uint4*)(args.res_hi + o_base + c0);
+                a0 = __ldg(rp); a1 = __ldg(rp + 1);
+                if (has_res_lo) {
+                    const uint4* lp = (const uint4*)(args.res_lo + o_base + c0);
+                    b0 = __ldg(lp); b1 = __ldg(lp + 1);
+                }
+            }
+        };
+        load_res(0, rh0, rh1, rl0, rl1);
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            float v[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after per-row predication
+            tmem_ld16(t_addr + c0, v);
+            uint4 nh0, nh1, nl0, nl1;
+            nh0 = nh1 = nl0 = nl1 = make_uint4(0, 0, 0, 0);
+            if (c0 + 16 < BLOCK_N) load_res(c0 + 16, nh0, nh1, nl0, nl1);
+            const int n = n_base + c0;
+            if (n < args.cout && row_ok) {
+                const bool full16 = (n + 16 <= args.cout);
+                if (args.scale) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (full16 || n + i < args.cout) v[i] *= __ldg(args.scale + n + i);
+                }
+                if (args.shift) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) if (full16 || n + i < args.cout) v[i] += __ldg(args.shift + n + i);
+                }
+                if (has_res && full16) {
+                    const uint32_t w[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        v[2 * i] += dec16<F16>((uint16_t)(w[i] & 0xFFFF));
+                        v[2 * i + 1] += dec16<F16>((uint16_t)(w[i] >> 16));
+                    }
+                    if (has_res_lo) {
+                        const uint32_t x[8] = {rl0.x, rl0.y, rl0.z, rl0.w, rl1.x, rl1.y, rl1.z, rl1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            v[2 * i] += dec16<F16>((uint16_t)(x[i] & 0xFFFF));
+                            v[2 * i + 1] += dec16<F16>((uint16_t)(x[i] >> 16));
+                        }
+                    }
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                const int64_t o = o_base + c0;
+                if (args.out_f32) {
+                    if (full16 && ((o & 3) == 0)) {
+                        float4* op = (float4*)(args.out_f32 + o);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) args.out_f32[o + i] = v[i];
+                    }
+                }
+                if (args.out_hi) {
+                    if (full16 && ((o & 7) == 0)) {
+                        uint32_t h[8], l[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) split2<F16>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                        uint4* op = (uint4*)(args.out_hi + o);
+                        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                        if (args.out_lo) {
+                            uint4* lp = (uint4*)(args.out_lo + o);
+                            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                        }
+                    } else {
+                        uint16_t* oh = (uint16_t*)args.out_hi;
+                        uint16_t* ol = (uint16_t*)args.out_lo;
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
+                            const uint16_t h0 = enc16<F16>(v[i]);
+                            oh[o + i] = h0;
+                            if (ol) ol[o + i] = enc16<F16>(v[i] - dec16<F16>(h0));
+                        }
+                    }
+                }
+            }
+            rh0 = nh0; rh1 = nh1; rl0 = nl0; rl1 = nl1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+}
+
 template <int BLOCK_N, int NA, int NB>
 __global__ void __launch_bounds__(CG_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
@@ -116,7 +233,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(CG_BLOCK_M, BLOCK_N);
+            const uint32_t idesc = args.f16 ? umma_idesc_f16(CG_BLOCK_M, BLOCK_N) : umma_idesc_bf16(CG_BLOCK_M, BLOCK_N);
             int st = 0; uint32_t ph = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
@@ -146,106 +263,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-            const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
-            const int acc = it & 1;
-            const uint32_t acc_ph = (it >> 1) & 1;
-            mbar_wait(&tfull[acc], acc_ph);
-            tc_fence_after();
-            const int64_t row = (int64_t)mt * CG_BLOCK_M + r;
-            const bool row_ok = row < args.m_total;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                float v[16];
-                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after per-row predication
-                tmem_ld16(t_addr + c0, v);
-                const int n = nt * BLOCK_N + c0;
-                if (n >= args.cout) continue;  // warp-uniform
-                if (args.scale) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] = v[i] * __ldg(args.scale + n + i);
-                }
-                if (args.shift) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] = v[i] + __ldg(args.shift + n + i);
-                }
-                if (!row_ok) continue;
-                const int64_t o = row * args.cout + n;
-                const bool full16 = (n + 16 <= args.cout);
-                if (args.res_hi) {
-                    if (full16) {
-                        const uint4* rp = (const uint4*)(args.res_hi + o);
-                        uint4 a = __ldg(rp), b = __ldg(rp + 1);
-                        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            v[2 * i] += __uint_as_float(w[i] << 16);
-                            v[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
-                        }
-                        if (args.res_lo) {
-                            const uint4* lp = (const uint4*)(args.res_lo + o);
-                            uint4 c = __ldg(lp), d = __ldg(lp + 1);
-                            const uint32_t x[8] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                v[2 * i] += __uint_as_float(x[i] << 16);
-                                v[2 * i + 1] += __uint_as_float(x[i] & 0xFFFF0000u);
-                            }
-                        }
-                    } else {
-                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
-                            v[i] += __bfloat162float(args.res_hi[o + i]);
-                            if (args.res_lo) v[i] += __bfloat162float(args.res_lo[o + i]);
-                        }
-                    }
-                }
-                if (args.relu) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
-                }
-                if (args.out_f32) {
-                    if (full16 && ((o & 3) == 0)) {
-                        float4* op = (float4*)(args.out_f32 + o);
-#pragma unroll
-                        for (int i = 0; i < 4; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    } else {
-                        for (int i = 0; i < 16; i++) if (n + i < args.cout) args.out_f32[o + i] = v[i];
-                    }
-                }
-                if (args.out_hi) {
-                    if (full16 && ((o & 7) == 0)) {
-                        uint32_t h[8], l[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const bf16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-                            h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            if (args.out_lo) l[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
-                        }
-                        uint4* op = (uint4*)(args.out_hi + o);
-                        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                        if (args.out_lo) {
-                            uint4* lp = (uint4*)(args.out_lo + o);
-                            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
-                            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
-                        }
-                    } else {
-                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
-                            const bf16 h0 = __float2bfloat16_rn(v[i]);
-                            args.out_hi[o + i] = h0;
-                            if (args.out_lo) args.out_lo[o + i] = __float2bfloat16_rn(v[i] - __bfloat162float(h0));
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
+        if (args.f16) epilogue<BLOCK_N, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+        else epilogue<BLOCK_N, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
     }
     tc_fence_before();
     __syncthreads();

@@ -148,7 +148,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
                              int out_layout, int32_t* status, void* stream) {
     if (!ctx || !frames || !boxes || !out || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
     if (out_size <= 0 || out_size > 1024 || padding < 0) return PA_ERR_INVALID_ARG;
-    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_BF16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4)
+    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4)
         return PA_ERR_INVALID_ARG;
     if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
     if (n_crops == 0) return PA_OK;
@@ -227,7 +227,7 @@ struct PlanOp {
     // pools
     const bf16 *pin_hi, *pin_lo;
     bf16 *pout_hi, *pout_lo;
-    int pn, ph, pw, pc;
+    int pn, ph, pw, pc, pf16;
 };
 
 struct pa_model {
@@ -268,6 +268,53 @@ static inline float bf2f(uint16_t h) {
     memcpy(&f, &u, 4);
     return f;
 }
+
+// IEEE binary16, round-to-nearest-even, with subnormals and saturation to +-65504
+static inline uint16_t f2h(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    u &= 0x7FFFFFFFu;
+    if (u > 0x7F800000u) return (uint16_t)(sign | 0x7E00u);  // NaN
+    if (u >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);  // >= 65520 rounds past max: saturate
+    if (u < 0x38800000u) {  // subnormal half (|f| < 2^-14)
+        if (u < 0x33000000u) return (uint16_t)sign;  // < 2^-25: rounds to zero
+        const int e = (int)(u >> 23);  // biased float exponent
+        uint32_t m = (u & 0x7FFFFFu) | 0x800000u;
+        const int shift = 126 - e;  // bits to drop so that 2^-24 is the unit
+        const uint32_t half = 1u << (shift - 1);
+        const uint32_t rem = m & ((1u << shift) - 1);
+        m >>= shift;
+        if (rem > half || (rem == half && (m & 1))) m++;
+        return (uint16_t)(sign | m);
+    }
+    uint32_t v = u - 0x38000000u;  // rebias exponent 127 -> 15
+    const uint32_t rem = v & 0x1FFFu;
+    v >>= 13;
+    if (rem > 0x1000u || (rem == 0x1000u && (v & 1))) v++;
+    return (uint16_t)(sign | v);
+}
+static inline float h2f(uint16_t h) {
+    const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
+    uint32_t e = (h >> 10) & 0x1F, m = h & 0x3FF, u;
+    if (e == 0) {
+        if (m == 0) u = sign;
+        else {
+            int s = 0;
+            while (!(m & 0x400)) { m <<= 1; s++; }
+            m &= 0x3FF;
+            u = sign | ((uint32_t)(113 - s) << 23) | (m << 13);
+        }
+    } else if (e == 31) u = sign | 0x7F800000u | (m << 13);
+    else u = sign | ((e + 112) << 23) | (m << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static inline bool prec_f16(int p) { return p >= PA_PREC_F16; }
+static inline bool prec_split(int p) { return p == PA_PREC_BF16X2 || p == PA_PREC_BF16X3 || p == PA_PREC_F16X2 || p == PA_PREC_F16X3; }
+static inline bool prec_split_w(int p) { return p == PA_PREC_BF16X3 || p == PA_PREC_F16X3; }
 
 extern "C" int pa_model_create(pa_ctx* ctx, int n_actions, int seq_len, pa_model** out) {
     if (!ctx || !out || n_actions <= 0 || n_actions > 128 || seq_len <= 0 || seq_len > 15 || (seq_len % 2) == 0) return PA_ERR_INVALID_ARG;
@@ -315,11 +362,16 @@ static int upload(pa_model* m, const std::vector<T>& host, T** dev) {
     return PA_OK;
 }
 
-static void split_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+static void split_weights(const std::vector<float>& w, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, bool f16) {
     hi.resize(w.size()); lo.resize(w.size());
     for (size_t i = 0; i < w.size(); i++) {
-        hi[i] = f2bf(w[i]);
-        lo[i] = f2bf(w[i] - bf2f(hi[i]));
+        if (f16) {
+            hi[i] = f2h(w[i]);
+            lo[i] = f2h(w[i] - h2f(hi[i]));
+        } else {
+            hi[i] = f2bf(w[i]);
+            lo[i] = f2bf(w[i] - bf2f(hi[i]));
+        }
     }
 }
 
@@ -335,10 +387,10 @@ static int prepare_conv(pa_model* m, ConvLayer& L) {
             for (int t = 0; t < taps; t++)
                 packed[((size_t)o * taps + t) * L.cin + c] = w->data[((size_t)o * L.cin + c) * taps + t];
     std::vector<uint16_t> hi, lo;
-    split_weights(packed, hi, lo);
+    split_weights(packed, hi, lo, prec_f16(m->precision));
     int rc = upload(m, hi, (uint16_t**)&L.w_hi);
     if (rc != PA_OK) return rc;
-    if (m->precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
+    if (prec_split_w(m->precision)) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
     std::vector<float> scale(L.cout, 1.f), shift(L.cout, 0.f);
     if (!L.bn_key.empty()) {
         const HostTensor *g = get_tensor(m, L.bn_key + ".weight", {L.cout}), *b = get_tensor(m, L.bn_key + ".bias", {L.cout}),
@@ -368,7 +420,7 @@ static ConvLayer make_conv(const std::string& w, const std::string& bn, int cin,
 
 extern "C" int pa_model_finalize(pa_model* m, int precision) {
     if (!m) return PA_ERR_INVALID_ARG;
-    if (precision < PA_PREC_BF16 || precision > PA_PREC_BF16X3) return PA_ERR_INVALID_ARG;
+    if (precision < PA_PREC_BF16 || precision > PA_PREC_F16X3) return PA_ERR_INVALID_ARG;
     pa_ctx* ctx = m->ctx;
     PA_CUDA(ctx, cudaSetDevice(ctx->device));
     for (void* p : m->dev_allocs) cudaFree(p);
@@ -389,10 +441,10 @@ extern "C" int pa_model_finalize(pa_model* m, int precision) {
                     for (int kx = 0; kx < 7; kx++)
                         packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w->data[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
         std::vector<uint16_t> hi, lo;
-        split_weights(packed, hi, lo);
+        split_weights(packed, hi, lo, prec_f16(precision));
         rc = upload(m, hi, (uint16_t**)&m->stem_w_hi); if (rc != PA_OK) return rc;
         m->stem_w_lo = nullptr;
-        if (precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&m->stem_w_lo); if (rc != PA_OK) return rc; }
+        if (prec_split_w(precision)) { rc = upload(m, lo, (uint16_t**)&m->stem_w_lo); if (rc != PA_OK) return rc; }
         m->stem = make_conv("", P + "bn1", 3, 64, 7, 2, 3, 128, true);
         ConvLayer& L = m->stem;
         const HostTensor *g = get_tensor(m, L.bn_key + ".weight", {64}), *b = get_tensor(m, L.bn_key + ".bias", {64}),
@@ -444,12 +496,12 @@ extern "C" int pa_model_finalize(pa_model* m, int precision) {
             for (int i = 0; i < 1000; i++)
                 for (int t = 0; t < S; t++) packed[((size_t)t * 512 + o) * 1000 + i] = w->data[((size_t)o * 1000 + i) * S + t];
         std::vector<uint16_t> hi, lo;
-        split_weights(packed, hi, lo);
+        split_weights(packed, hi, lo, prec_f16(precision));
         ConvLayer& L = m->proj;
         L = make_conv("", "", 1000, S * 512, 1, 1, 0, 1, false);
         L.k_total = 1000;
         rc = upload(m, hi, (uint16_t**)&L.w_hi); if (rc != PA_OK) return rc;
-        if (precision == PA_PREC_BF16X3) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
+        if (prec_split_w(precision)) { rc = upload(m, lo, (uint16_t**)&L.w_lo); if (rc != PA_OK) return rc; }
         rc = upload(m, b->data, &m->b1d); if (rc != PA_OK) return rc;
     }
     // ---- classifier MLP (fp32 SIMT in the head kernel), weights transposed for coalesced reads
@@ -478,7 +530,7 @@ static const size_t kSmallElems = (size_t)32 * 32 * 64;  // per crop
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t features_ws_bytes(const pa_model* m, int n) {
-    const int planes = (m->precision == PA_PREC_BF16) ? 1 : 2;
+    const int planes = prec_split(m->precision) ? 2 : 1;
     size_t per_plane = align256(kBigElems * n * 2) + 4 * align256(kSmallElems * n * 2) + align256((size_t)n * 512 * 2);
     return per_plane * planes + 1024;
 }
@@ -583,12 +635,14 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.out_hi = out ? out->hi : nullptr;
     a.out_lo = out ? out->lo : nullptr;
     a.out_f32 = out_f32;
+    a.f16 = prec_f16(m->precision) ? 1 : 0;
     return PA_OK;
 }
 
 static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat, void* ws, size_t ws_bytes) {
     if (features_ws_bytes(m, n) > ws_bytes) return PA_ERR_WORKSPACE;
-    const bool split = m->precision != PA_PREC_BF16;
+    const bool split = prec_split(m->precision);
+    const int f16 = prec_f16(m->precision) ? 1 : 0;
     uint8_t* p = (uint8_t*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     auto carve = [&](size_t elems) {
         Act a;
@@ -612,6 +666,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         op.c1.scale = m->stem.scale; op.c1.shift = m->stem.shift;
         op.c1.out_hi = big.hi; op.c1.out_lo = big.lo;
         op.c1.n_crops = n;
+        op.c1.f16 = f16;
         m->plan.push_back(op);
     }
     {
@@ -619,7 +674,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         op.kind = 1;
         snprintf(op.name, sizeof(op.name), "maxpool");
         op.pin_hi = big.hi; op.pin_lo = big.lo; op.pout_hi = sm[0].hi; op.pout_lo = sm[0].lo;
-        op.pn = n; op.ph = 64; op.pw = 64; op.pc = 64;
+        op.pn = n; op.ph = 64; op.pw = 64; op.pc = 64; op.pf16 = f16;
         m->plan.push_back(op);
     }
     int x = 0;  // index of the buffer holding the block input
@@ -650,7 +705,7 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         op.kind = 3;
         snprintf(op.name, sizeof(op.name), "avgpool");
         op.pin_hi = sm[x].hi; op.pin_lo = sm[x].lo; op.pout_hi = pooled.hi; op.pout_lo = pooled.lo;
-        op.pn = n; op.ph = 16; op.pc = 512;
+        op.pn = n; op.ph = 16; op.pc = 512; op.pf16 = f16;
         m->plan.push_back(op);
     }
     {
@@ -678,9 +733,9 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
         ProfSpan sp(ctx, op.name, st);
         switch (op.kind) {
             case 0: rc = launch_conv1(op.c1, ctx->num_sms, st); break;
-            case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, st); break;
+            case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
             case 2: rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st); break;
-            case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, st); break;
+            case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
         }
         if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "feature kernel launch") : rc;
         ctx->launches += 1;
@@ -695,7 +750,7 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
     pa_ctx* ctx = m->ctx;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_ws_bytes(m, n_feat) > workspace_bytes) return PA_ERR_WORKSPACE;
-    const bool split = m->precision != PA_PREC_BF16;
+    const bool split = prec_split(m->precision);
     uint8_t* p = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     Act fb;
     fb.hi = (bf16*)p; p += align256((size_t)n_feat * 1000 * 2);
@@ -710,7 +765,7 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
     int rc;
     {
         ProfSpan sp(ctx, "feat_to_bf16", st);
-        rc = launch_split_f32(feat, fb.hi, fb.lo, (int64_t)n_feat * 1000, st);
+        rc = launch_split_f32(feat, fb.hi, fb.lo, (int64_t)n_feat * 1000, prec_f16(m->precision) ? 1 : 0, st);
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "split launch");
     const PlanOp& g = m->head_gemm;
@@ -735,9 +790,11 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
 // ------------------------------------------------------------------------------------------------ single-layer entry points
 // One convolution / the stem on caller-provided NHWC bf16 activations and host fp32 weights.
 // Used by the layer-level parity tests (tests/test_gpu_layers.py); synchronous, allocates scratch.
-static int layer_model(pa_ctx* ctx, int split_w, pa_model& m) {
+// flags: bit 0 = split the weights too (3 MMAs), bit 1 = IEEE-half operands instead of bf16
+static int layer_model(pa_ctx* ctx, int flags, pa_model& m) {
     m.ctx = ctx;
-    m.precision = split_w ? PA_PREC_BF16X3 : PA_PREC_BF16;
+    const bool f16 = (flags & 2) != 0, sw = (flags & 1) != 0;
+    m.precision = f16 ? (sw ? PA_PREC_F16X3 : PA_PREC_F16) : (sw ? PA_PREC_BF16X3 : PA_PREC_BF16);
     return PA_OK;
 }
 
@@ -746,7 +803,7 @@ extern "C" int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int 
                          const void* res_hi, const void* res_lo, int relu, void* out_hi, void* out_lo, float* out_f32,
                          int split_w, void* stream) {
     if (!ctx || !in_hi || !w_host || n <= 0 || (!out_hi && !out_f32)) return PA_ERR_INVALID_ARG;
-    if (split_w && !in_lo) return PA_ERR_INVALID_ARG;
+    if ((split_w & 1) && !in_lo) return PA_ERR_INVALID_ARG;
     pa_model m;
     layer_model(ctx, split_w, m);
     HostTensor t;
@@ -781,7 +838,7 @@ extern "C" int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int 
 extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n, const float* w_host /*[64][3][7][7]*/,
                        const float* scale_host, const float* shift_host, void* out_hi, void* out_lo, int split_w, void* stream) {
     if (!ctx || !in_hi || !w_host || !scale_host || !shift_host || !out_hi || n <= 0) return PA_ERR_INVALID_ARG;
-    if (split_w && !in_lo) return PA_ERR_INVALID_ARG;
+    if ((split_w & 1) && !in_lo) return PA_ERR_INVALID_ARG;
     pa_model m;
     layer_model(ctx, split_w, m);
     std::vector<float> packed((size_t)64 * 256, 0.f);
@@ -791,12 +848,12 @@ extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n,
                 for (int kx = 0; kx < 7; kx++)
                     packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w_host[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
     std::vector<uint16_t> hi, lo;
-    split_weights(packed, hi, lo);
+    split_weights(packed, hi, lo, prec_f16(m.precision));
     std::vector<float> sc(scale_host, scale_host + 64), sh(shift_host, shift_host + 64);
     Conv1Args a;
     memset(&a, 0, sizeof(a));
     int rc = upload(&m, hi, (uint16_t**)&a.w_hi);
-    if (rc == PA_OK && split_w) rc = upload(&m, lo, (uint16_t**)&a.w_lo);
+    if (rc == PA_OK && (split_w & 1)) rc = upload(&m, lo, (uint16_t**)&a.w_lo);
     float *dsc = nullptr, *dsh = nullptr;
     if (rc == PA_OK) rc = upload(&m, sc, &dsc);
     if (rc == PA_OK) rc = upload(&m, sh, &dsh);
@@ -805,6 +862,7 @@ extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n,
         a.scale = dsc; a.shift = dsh;
         a.out_hi = (bf16*)out_hi; a.out_lo = (bf16*)out_lo;
         a.n_crops = n;
+        a.f16 = prec_f16(m.precision) ? 1 : 0;
         rc = launch_conv1(a, ctx->num_sms, (cudaStream_t)stream);
         if (rc == PA_OK) {
             ctx->launches += 1;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,6 +55,7 @@ struct ConvArgs {
     bf16* out_hi;         // bf16 output [M][cout] or nullptr
     bf16* out_lo;         // lo plane (split precision) or nullptr
     float* out_f32;       // fp32 output [M][cout] or nullptr
+    int f16;              // 16-bit operand format: 0 bf16, 1 IEEE half
 };
 
 int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms,
@@ -72,15 +74,16 @@ struct Conv1Args {
     bf16* out_hi;         // [n][64][64][64]
     bf16* out_lo;         // or nullptr
     int n_crops;
+    int f16;              // 0 bf16, 1 IEEE half
 };
 int launch_conv1(const Conv1Args& a, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small memory-bound kernels
 int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
+                   int f16, cudaStream_t stream);
+int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c, int f16,
                    cudaStream_t stream);
-int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c,
-                   cudaStream_t stream);
-int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, cudaStream_t stream);
+int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int f16, cudaStream_t stream);
 
 struct HeadArgs {
     const float* proj;     // [n_feat][seq*512] per-frame temporal projections

@@ -265,15 +265,22 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
         }
         return;
     }
-    // bf16 (optionally with a lo plane holding the rounding residual)
-    __nv_bfloat16 hi[3], lo[3];
+    // 16-bit float (bf16 or IEEE half), optionally with a lo plane holding the rounding residual
+    const bool f16 = (p.out_dtype == PA_DTYPE_F16 || p.out_dtype == PA_DTYPE_F16X2);
+    uint16_t hi[3], lo[3];
     for (int c = 0; c < 3; c++) {
-        hi[c] = __float2bfloat16_rn(fv[c]);
-        lo[c] = __float2bfloat16_rn(__fsub_rn(fv[c], __bfloat162float(hi[c])));
+        if (f16) {
+            const __half h = __float2half_rn(fv[c]);
+            hi[c] = __half_as_ushort(h);
+            lo[c] = __half_as_ushort(__float2half_rn(__fsub_rn(fv[c], __half2float(h))));
+        } else {
+            const __nv_bfloat16 h = __float2bfloat16_rn(fv[c]);
+            hi[c] = __bfloat16_as_ushort(h);
+            lo[c] = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(fv[c], __bfloat162float(h))));
+        }
     }
-    __nv_bfloat16* o = (__nv_bfloat16*)p.outp;
-    const bool split = p.out_dtype == PA_DTYPE_BF16X2;
-    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    uint16_t* o = (uint16_t*)p.outp;
+    const bool split = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2);
     if (p.out_layout == PA_LAYOUT_NCHW) {
         for (int c = 0; c < 3; c++) {
             int64_t i = (((int64_t)crop * 3 + c) * out + f) * out + dx;
@@ -283,12 +290,12 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
     } else if (p.out_layout == PA_LAYOUT_NHWC4) {
         int64_t i = (((int64_t)crop * out + f) * out + dx) * 4;
         uint2 q;
-        q.x = (uint32_t)__bfloat16_as_ushort(hi[0]) | ((uint32_t)__bfloat16_as_ushort(hi[1]) << 16);
-        q.y = (uint32_t)__bfloat16_as_ushort(hi[2]) | ((uint32_t)__bfloat16_as_ushort(z) << 16);
+        q.x = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16);
+        q.y = (uint32_t)hi[2];
         *(uint2*)(o + i) = q;
         if (split) {
-            q.x = (uint32_t)__bfloat16_as_ushort(lo[0]) | ((uint32_t)__bfloat16_as_ushort(lo[1]) << 16);
-            q.y = (uint32_t)__bfloat16_as_ushort(lo[2]) | ((uint32_t)__bfloat16_as_ushort(z) << 16);
+            q.x = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16);
+            q.y = (uint32_t)lo[2];
             *(uint2*)(o + p.plane_elems + i) = q;
         }
     } else {
@@ -305,7 +312,7 @@ __device__ void zero_rows(const PPParams& p, int crop, int F0, int F1) {
     const int out = p.out;
     int esz = (p.out_dtype == PA_DTYPE_U8) ? 1 : (p.out_dtype == PA_DTYPE_F32 ? 4 : 2);
     int ch = (p.out_layout == PA_LAYOUT_NHWC4) ? 4 : 3;
-    int nplanes = (p.out_dtype == PA_DTYPE_BF16X2) ? 2 : 1;
+    int nplanes = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2) ? 2 : 1;
     for (int pl = 0; pl < nplanes; pl++) {
         uint8_t* base = (uint8_t*)p.outp + (int64_t)pl * p.plane_elems * esz;
         if (p.out_layout == PA_LAYOUT_NCHW) {

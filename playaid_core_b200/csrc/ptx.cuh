@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -122,6 +123,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with IEEE-half operands (A/B format 0 = F16).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by one thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -154,6 +159,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16-bit activation formats: F16 == false -> bfloat16, true -> IEEE half (saturating).
+template <bool F16>
+__device__ __forceinline__ uint16_t enc16(float v) {
+    if (F16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <bool F16>
+__device__ __forceinline__ float dec16(uint16_t b) {
+    if (F16) return __half2float(__ushort_as_half(b));
+    return __uint_as_float((uint32_t)b << 16);
+}
+// v -> (hi, lo) pair packed for two neighbouring elements
+template <bool F16>
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const uint16_t h0 = enc16<F16>(v0), h1 = enc16<F16>(v1);
+    hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    lo = (uint32_t)enc16<F16>(v0 - dec16<F16>(h0)) | ((uint32_t)enc16<F16>(v1 - dec16<F16>(h1)) << 16);
 }
 
 }  // namespace pa

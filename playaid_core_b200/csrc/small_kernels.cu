@@ -5,13 +5,15 @@
 // SpatialStreamCNN.cnn1d + classifier (:22-27,37-41); CNNActionDetector.forward log_softmax (:92);
 // AIRunner.action_recognition argmax / exp (playaid/ai_runner.py:474-477).
 #include "pa_internal.cuh"
+#include "ptx.cuh"
 
 namespace pa {
 
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+template <bool F16> __device__ __forceinline__ float el_lo(uint32_t w) { return dec16<F16>((uint16_t)(w & 0xFFFF)); }
+template <bool F16> __device__ __forceinline__ float el_hi(uint32_t w) { return dec16<F16>((uint16_t)(w >> 16)); }
 
 // ---------------------------------------------------------------- maxpool 3x3 stride 2 pad 1 (NHWC, C % 8 == 0)
+template <bool F16>
 __global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
                                bf16* __restrict__ out_lo, int n, int hin, int win, int c) {
     const int ho = hin / 2, wo = win / 2, cg = c / 8;
@@ -25,7 +27,7 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
         float best[8];
         uint16_t bh[8], bl[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { best[k] = -INFINITY; bh[k] = 0xFF80; bl[k] = 0; }
+        for (int k = 0; k < 8; k++) { best[k] = -INFINITY; bh[k] = F16 ? 0xFC00 : 0xFF80; bl[k] = 0; }
         for (int dy = -1; dy <= 1; dy++) {
             const int iy = 2 * oy + dy;
             if (iy < 0 || iy >= hin) continue;
@@ -39,7 +41,7 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
                 const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const float v0 = bf_lo(hw[k]) + bf_lo(lw[k]), v1 = bf_hi(hw[k]) + bf_hi(lw[k]);
+                    const float v0 = el_lo<F16>(hw[k]) + el_lo<F16>(lw[k]), v1 = el_hi<F16>(hw[k]) + el_hi<F16>(lw[k]);
                     if (v0 > best[2 * k]) { best[2 * k] = v0; bh[2 * k] = (uint16_t)(hw[k] & 0xFFFF); bl[2 * k] = (uint16_t)(lw[k] & 0xFFFF); }
                     if (v1 > best[2 * k + 1]) { best[2 * k + 1] = v1; bh[2 * k + 1] = (uint16_t)(hw[k] >> 16); bl[2 * k + 1] = (uint16_t)(lw[k] >> 16); }
                 }
@@ -59,16 +61,18 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
 }
 
 int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
-                   cudaStream_t stream) {
+                   int f16, cudaStream_t stream) {
     const int64_t total = (int64_t)n * (hin / 2) * (win / 2) * (c / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    maxpool_kernel<<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
+    if (f16) maxpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
+    else maxpool_kernel<false><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------- global average pool [n][hw][c] -> [n][c]
+template <bool F16>
 __global__ void avgpool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
                                bf16* __restrict__ out_lo, int n, int hw, int c) {
     const int64_t total = (int64_t)n * c;
@@ -79,41 +83,45 @@ __global__ void avgpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
         float s = 0.f;
         for (int p = 0; p < hw; p++) {
             const int64_t off = (b * hw + p) * c + ch;
-            float v = __bfloat162float(in_hi[off]);
-            if (in_lo) v += __bfloat162float(in_lo[off]);
+            float v = dec16<F16>(((const uint16_t*)in_hi)[off]);
+            if (in_lo) v += dec16<F16>(((const uint16_t*)in_lo)[off]);
             s += v;
         }
         s *= inv;
-        const bf16 h = __float2bfloat16_rn(s);
-        out_hi[i] = h;
-        if (out_lo) out_lo[i] = __float2bfloat16_rn(s - __bfloat162float(h));
+        const uint16_t h = enc16<F16>(s);
+        ((uint16_t*)out_hi)[i] = h;
+        if (out_lo) ((uint16_t*)out_lo)[i] = enc16<F16>(s - dec16<F16>(h));
     }
 }
 
-int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c, cudaStream_t stream) {
+int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c, int f16,
+                   cudaStream_t stream) {
     const int64_t total = (int64_t)n * c;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    avgpool_kernel<<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
+    if (f16) avgpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
+    else avgpool_kernel<false><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------- fp32 -> bf16 hi (+ lo)
+template <bool F16>
 __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int64_t n) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = in[i];
-        const bf16 h = __float2bfloat16_rn(v);
-        out_hi[i] = h;
-        if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const uint16_t h = enc16<F16>(v);
+        ((uint16_t*)out_hi)[i] = h;
+        if (out_lo) ((uint16_t*)out_lo)[i] = enc16<F16>(v - dec16<F16>(h));
     }
 }
 
-int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, cudaStream_t stream) {
+int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int f16, cudaStream_t stream) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    split_kernel<<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
+    if (f16) split_kernel<true><<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
+    else split_kernel<false><<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

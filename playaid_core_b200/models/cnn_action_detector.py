@@ -20,7 +20,14 @@ import torch
 
 from .. import _lib
 
-PRECISIONS = {"bf16": _lib.PREC_BF16, "bf16x2": _lib.PREC_BF16X2, "bf16x3": _lib.PREC_BF16X3}
+# name -> (native precision id, activations split hi+lo, IEEE half instead of bfloat16)
+#   bf16 / f16       one tensor-core product per k-step (f16: 11-bit significand, same rate as bf16)
+#   bf16x2 / f16x2   activations carry a rounding-residual plane: 2 products (f16x2 ~ fp32 accuracy)
+#   bf16x3 / f16x3   weights split as well: 3 products, for checkpoints that are not 16-bit exact
+PRECISIONS = {
+    "bf16": (_lib.PREC_BF16, False, False), "bf16x2": (_lib.PREC_BF16X2, True, False), "bf16x3": (_lib.PREC_BF16X3, True, False),
+    "f16": (_lib.PREC_F16, False, True), "f16x2": (_lib.PREC_F16X2, True, True), "f16x3": (_lib.PREC_F16X3, True, True),
+}
 
 
 class SpatialStreamCNN:
@@ -44,7 +51,7 @@ class CNNActionDetector:
         learning_rate: float = 2e-4,
         num_samples: int = 1024,
         freeze_encoder=False,
-        precision: str = "bf16",
+        precision: str = "f16",
         device=None,
         **kwargs,
     ):
@@ -126,7 +133,7 @@ class CNNActionDetector:
             shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
             _lib.check(lib.pa_model_set_tensor(h, k.encode(), a.ctypes.data, shape, a.ndim), self._ctx.handle, f"set_tensor {k}")
         with torch.cuda.device(self._device):
-            _lib.check(lib.pa_model_finalize(h, PRECISIONS[self.precision]), self._ctx.handle, "pa_model_finalize")
+            _lib.check(lib.pa_model_finalize(h, PRECISIONS[self.precision][0]), self._ctx.handle, "pa_model_finalize")
         self._handle = h
 
     def __del__(self):
@@ -139,11 +146,21 @@ class CNNActionDetector:
     # ------------------------------------------------------------------ native halves
     @property
     def split(self) -> bool:
-        return self.precision != "bf16"
+        return PRECISIONS[self.precision][1]
+
+    @property
+    def half(self) -> bool:
+        return PRECISIONS[self.precision][2]
+
+    @property
+    def act_dtype(self) -> torch.dtype:
+        return torch.float16 if self.half else torch.bfloat16
 
     @property
     def crop_dtype(self) -> int:
         """pa_preprocess out_dtype that matches this model's arithmetic."""
+        if self.half:
+            return _lib.DTYPE_F16X2 if self.split else _lib.DTYPE_F16
         return _lib.DTYPE_BF16X2 if self.split else _lib.DTYPE_BF16
 
     def _workspace(self, n: int) -> torch.Tensor:
@@ -154,13 +171,14 @@ class CNNActionDetector:
         return self._ws
 
     def features(self, crops: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """crops: bf16 CUDA NHWC4 [n,128,128,4] (or [2,n,128,128,4] hi/lo planes in split precision),
-        as written by `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4)` -> fp32 [n,1000]."""
+        """crops: 16-bit (self.act_dtype) CUDA NHWC4 [n,128,128,4] (or [2,n,128,128,4] hi/lo planes in
+        split precision), as written by `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4)`
+        -> fp32 [n,1000]."""
         if self._handle is None:
             raise _lib.PlayaidLibraryError("no weights loaded: call load_state_dict / load_from_checkpoint first")
         want = 5 if self.split else 4
-        if crops.dtype != torch.bfloat16 or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 128, 4):
-            raise ValueError("crops must be contiguous bf16 NHWC4 [n,128,128,4] ([2,n,...] planes in split precision)")
+        if crops.dtype != self.act_dtype or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 128, 4):
+            raise ValueError(f"crops must be contiguous {self.act_dtype} NHWC4 [n,128,128,4] ([2,n,...] planes in split precision)")
         n = int(crops.shape[-4])
         if out is None:
             out = torch.empty((n, 1000), dtype=torch.float32, device=crops.device)
@@ -201,9 +219,9 @@ class CNNActionDetector:
         x = x.to(self._device, torch.float32).reshape(B * S, 3, H, W).permute(0, 2, 3, 1)
         x4 = torch.zeros((B * S, H, W, 4), dtype=torch.float32, device=self._device)
         x4[..., :3] = x
-        hi = x4.to(torch.bfloat16)
+        hi = x4.to(self.act_dtype)
         if self.split:
-            lo = (x4 - hi.float()).to(torch.bfloat16)
+            lo = (x4 - hi.float()).to(self.act_dtype)
             crops = torch.stack([hi, lo]).contiguous()
         else:
             crops = hi.contiguous()

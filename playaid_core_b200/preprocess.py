@@ -16,7 +16,7 @@ from . import _lib
 from .fighter import yolo_pixels_batch
 
 _TORCH_DTYPE = {_lib.DTYPE_U8: torch.uint8, _lib.DTYPE_BF16: torch.bfloat16, _lib.DTYPE_F32: torch.float32,
-                _lib.DTYPE_BF16X2: torch.bfloat16}
+                _lib.DTYPE_BF16X2: torch.bfloat16, _lib.DTYPE_F16: torch.float16, _lib.DTYPE_F16X2: torch.float16}
 
 
 def crop_records(norm_boxes, frame_index, image_width: int, image_height: int) -> np.ndarray:
@@ -30,7 +30,7 @@ def crop_records(norm_boxes, frame_index, image_width: int, image_height: int) -
 
 
 def output_shape(n: int, out_size: int, dtype: int, layout: int):
-    planes = 2 if dtype == _lib.DTYPE_BF16X2 else 1
+    planes = 2 if dtype in (_lib.DTYPE_BF16X2, _lib.DTYPE_F16X2) else 1
     if layout == _lib.LAYOUT_NCHW:
         shp = (n, 3, out_size, out_size)
     elif layout == _lib.LAYOUT_NHWC4:

@@ -27,29 +27,33 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _conv(env, x, w, stride, pad, scale=None, shift=None, res=None, relu=False, split=False, out_bf16=False, split_w=False):
-    """x [N,C,H,W] fp32 (bf16-representable unless split), w [O,C,k,k] fp32. Returns NCHW fp32."""
+def _conv(env, x, w, stride, pad, scale=None, shift=None, res=None, relu=False, split=False, out_bf16=False, split_w=False,
+          half=False):
+    """x [N,C,H,W] fp32 (16-bit-representable unless split), w [O,C,k,k] fp32. Returns NCHW fp32.
+    half=True uses IEEE-half planes instead of bfloat16 (flag bit 1 of pa_conv2d)."""
     torch, _lib, ctx = env
+    dt = torch.float16 if half else torch.bfloat16
     N, C, H, _ = x.shape
     O, _, k, _ = w.shape
     Ho = H // stride
     xh = x.permute(0, 2, 3, 1).contiguous()
-    hi = xh.to(torch.bfloat16)
-    lo = (xh - hi.float()).to(torch.bfloat16) if split else None
+    hi = xh.to(dt)
+    lo = (xh - hi.float()).to(dt) if split else None
     rh = rl = None
     if res is not None:
         r = res.permute(0, 2, 3, 1).contiguous()
-        rh = r.to(torch.bfloat16)
-        rl = (r - rh.float()).to(torch.bfloat16) if split else None
+        rh = r.to(dt)
+        rl = (r - rh.float()).to(dt) if split else None
     out_f32 = None if out_bf16 else torch.full((N, Ho, Ho, O), float("nan"), device="cuda")
-    out_hi = torch.full((N, Ho, Ho, O), float("nan"), device="cuda", dtype=torch.bfloat16) if out_bf16 else None
+    out_hi = torch.full((N, Ho, Ho, O), float("nan"), device="cuda", dtype=dt) if out_bf16 else None
     out_lo = torch.zeros_like(out_hi) if (out_bf16 and split) else None
     wc = w.cpu().contiguous()
     sc = scale.cpu().contiguous() if scale is not None else None
     sh = shift.cpu().contiguous() if shift is not None else None
     rc = ctx.lib.pa_conv2d(ctx.handle, _ptr(hi), _ptr(lo), N, H, C, wc.data_ptr(), O, k, stride, pad,
                            sc.data_ptr() if sc is not None else None, sh.data_ptr() if sh is not None else None,
-                           _ptr(rh), _ptr(rl), 1 if relu else 0, _ptr(out_hi), _ptr(out_lo), _ptr(out_f32), 1 if split_w else 0,
+                           _ptr(rh), _ptr(rl), 1 if relu else 0, _ptr(out_hi), _ptr(out_lo), _ptr(out_f32),
+                           (1 if split_w else 0) | (2 if half else 0),
                            _lib.current_stream_ptr())
     _lib.check(rc, ctx.handle, "pa_conv2d")
     torch.cuda.synchronize()
@@ -142,29 +146,59 @@ def test_conv_split_precision_is_fp32_accurate(env):
     assert float((yb - ref).abs().max()) / float(ref.abs().max()) < 5e-5
 
 
+def test_conv_half_format(env):
+    """IEEE-half operand planes: plain (11-bit operands) and split hi+lo (~22 bits, fp32-level)."""
+    torch = env[0]
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((3, 128, 16, 16), device="cuda", generator=g)
+    w = _bf(torch, torch.randn((128, 128, 3, 3), device="cuda", generator=g) / 34)   # bf16-exact => half-exact
+    res = torch.randn((3, 128, 16, 16), device="cuda", generator=g)
+    scale = torch.rand(128, device="cuda", generator=g) + 0.5
+    shift = torch.randn(128, device="cuda", generator=g)
+    xh = x.half().float()
+    rh = res.half().float()
+    ref = _ref(torch, xh, w, 1, 1, scale, shift, rh, relu=True)
+    y = _conv(env, xh, w, 1, 1, scale, shift, rh, relu=True, half=True)
+    assert float((y - ref).abs().max()) / float(ref.abs().max()) < 1e-5
+    yb = _conv(env, xh, w, 1, 1, scale, shift, rh, relu=True, half=True, out_bf16=True)       # half output plane
+    assert float((yb - ref).abs().max()) / float(ref.abs().max()) < 1e-3
+    ref2 = _ref(torch, x, w, 1, 1, scale, shift, res, relu=True)
+    y2 = _conv(env, x, w, 1, 1, scale, shift, res, relu=True, half=True, split=True)            # hi+lo in
+    assert float((y2 - ref2).abs().max()) / float(ref2.abs().max()) < 3e-6
+    y2b = _conv(env, x, w, 1, 1, scale, shift, res, relu=True, half=True, split=True, out_bf16=True)  # hi+lo out
+    assert float((y2b - ref2).abs().max()) / float(ref2.abs().max()) < 3e-6
+    w32 = torch.randn((128, 128, 3, 3), device="cuda", generator=g) / 34
+    ref3 = _ref(torch, x, w32, 1, 1)
+    y3 = _conv(env, x, w32, 1, 1, half=True, split=True, split_w=True)                         # weights split too
+    assert float((y3 - ref3).abs().max()) / float(ref3.abs().max()) < 3e-6
+
+
+@pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("split", [False, True])
-def test_stem_vs_torch(env, split):
+def test_stem_vs_torch(env, split, half):
     torch, _lib, ctx = env
     g = torch.Generator(device="cuda").manual_seed(3)
     N = 5
     x = torch.rand((N, 3, 128, 128), device="cuda", generator=g)
+    dt = torch.float16 if half else torch.bfloat16
     if not split:
-        x = _bf(torch, x)
+        x = x.to(dt).float()
     w = _bf(torch, torch.randn((64, 3, 7, 7), device="cuda", generator=g) / 12)
     scale = torch.rand(64, device="cuda", generator=g) + 0.5
     shift = torch.randn(64, device="cuda", generator=g) * 0.1
     x4 = torch.zeros((N, 128, 128, 4), device="cuda")
     x4[..., :3] = x.permute(0, 2, 3, 1)
-    hi = x4.to(torch.bfloat16)
-    lo = (x4 - hi.float()).to(torch.bfloat16) if split else None
-    out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    hi = x4.to(dt)
+    lo = (x4 - hi.float()).to(dt) if split else None
+    out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=dt)
     out_lo = torch.zeros_like(out_hi) if split else None
     wc, sc, sh = w.cpu().contiguous(), scale.cpu().contiguous(), shift.cpu().contiguous()  # keep alive across the call
     rc = ctx.lib.pa_stem(ctx.handle, _ptr(hi), _ptr(lo), N, wc.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(out_hi),
-                         _ptr(out_lo), 0, _lib.current_stream_ptr())
+                         _ptr(out_lo), 2 if half else 0, _lib.current_stream_ptr())
     _lib.check(rc, ctx.handle, "pa_stem")
     torch.cuda.synchronize()
     y = (out_hi.float() + (out_lo.float() if split else 0)).permute(0, 3, 1, 2)
     ref = _ref(torch, x, w, 2, 3, scale, shift, relu=True)
     err = float((y - ref).abs().max()) / float(ref.abs().max())
-    assert torch.isfinite(y).all() and err < (5e-5 if split else 1e-2), err
+    tol = (3e-6 if half else 5e-5) if split else (1e-3 if half else 1e-2)
+    assert torch.isfinite(y).all() and err < tol, err

@@ -116,6 +116,11 @@ def test_output_formats(torch_cuda, golden_frames):
     hi, lo = x2[0, ..., :3].permute(0, 3, 1, 2).float(), x2[1, ..., :3].permute(0, 3, 1, 2).float()
     assert torch.equal(hi, want.to(torch.bfloat16).float())
     assert float((hi + lo - want).abs().max()) < 2e-5
+    h2, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F16X2, layout=_lib.LAYOUT_NHWC4)
+    hh, hl = h2[0, ..., :3].permute(0, 3, 1, 2), h2[1, ..., :3].permute(0, 3, 1, 2)
+    assert h2.dtype == torch.float16 and torch.equal(hh, want.half()) and float((hh.float() + hl.float() - want).abs().max()) < 2e-7
+    h1, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F16, layout=_lib.LAYOUT_NHWC4)
+    assert torch.equal(h1[..., :3].permute(0, 3, 1, 2), want.half())
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
     ms, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, mean=mean, std=std, dtype=_lib.DTYPE_F32, layout=_lib.LAYOUT_NCHW)
     m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)

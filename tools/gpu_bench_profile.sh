@@ -1,20 +1,35 @@
 #!/bin/bash
-# bench + ncu evidence on the GPU box. Usage: bash tools/gpu_bench_profile.sh <round-tag>
+# bench + ncu evidence on the GPU box. Usage: bash tools/gpu_bench_profile.sh <tag> [ncu-kernel-regex] [skip count]
 TAG=${1:-r01}
+KREGEX=${2:-"conv_gemm|conv1_kernel|preprocess"}
+SKIP=${3:-30}
+COUNT=${4:-14}
 mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
-echo "bench exit $?"; tail -c 3000 gpurun_out/bench_$TAG.json; tail -n 5 gpurun_out/bench_$TAG.err
-python bench.py --steps 10 --warmup 3 --precision bf16x2 --no-cpu-baseline > gpurun_out/bench_${TAG}_x2.json 2> gpurun_out/bench_${TAG}_x2.err
-echo "bench x2 exit $?"; tail -c 600 gpurun_out/bench_${TAG}_x2.json
+echo "bench exit $?"; tail -n 5 gpurun_out/bench_$TAG.err
+python bench.py --steps 10 --warmup 3 --precision f16x2 --no-cpu-baseline > gpurun_out/bench_${TAG}_f16x2.json 2> gpurun_out/bench_${TAG}_f16x2.err
+echo "bench f16x2 exit $?"
+python bench.py --steps 10 --warmup 3 --precision bf16 --no-cpu-baseline > gpurun_out/bench_${TAG}_bf16.json 2> gpurun_out/bench_${TAG}_bf16.err
+echo "bench bf16 exit $?"
 python bench.py --impl reference --steps 3 --warmup 0 > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err
-echo "reference exit $?"; cat gpurun_out/bench_${TAG}_reference.json
+echo "reference exit $?"
+python - <<PY
+import json
+for n in ["bench_$TAG","bench_${TAG}_f16x2","bench_${TAG}_bf16","bench_${TAG}_reference"]:
+    try:
+        d=json.load(open("gpurun_out/"+n+".json"))
+        print(n, "value=%.1f ms/step=%.3f e2e=%.1f launches=%s"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d.get("gpu_launches")))
+        if d.get("roofline"): print("   tensor frac %.3f  preprocess hbm frac %.4f"%(d["roofline"]["frac"], d["roofline_preprocess"]["frac"]))
+        ks=d.get("kernels") or {}
+        for k,v in sorted(ks.items(), key=lambda kv:-kv[1]["ms_per_step"])[:8]: print("   %-40s %.3f ms %.1f%%"%(k,v["ms_per_step"],100*v["share"]))
+    except Exception as e: print(n, "ERR", e)
+PY
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'preprocess|conv|maxpool|avgpool|head|split' -c 400 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'conv_gemm|conv1_kernel|preprocess' -s 30 -c 14 \
+ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s $SKIP -c $COUNT \
     -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full exit $?"
-ls -la gpurun_out | tail -20
