@@ -175,10 +175,12 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         status = ctx->pp_status;
     }
     p.status = status;
-    // pass 1: 100 KB of shared memory per CTA (2 CTAs / SM) covers windows up to ~600 px;
-    // pass 2: the few crops that did not fit are redone with the whole 227 KB carve-out.
-    p.smem_bytes = 100 * 1024;
+    // pass 1: 72 KB of shared memory per CTA (3 CTAs / SM) covers the usual fighter windows;
+    // pass 2: the few crops that did not fit are redone with the whole carve-out (1 CTA / SM).
+    PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
+    p.smem_bytes = 72 * 1024;
     p.first_pass_smem = 0;
+    p.defer_too_large = 1;
     int rc;
     {
         ProfSpan sp(ctx, "preprocess", (cudaStream_t)stream);
@@ -186,7 +188,8 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
     p.smem_bytes = 224 * 1024;
-    p.first_pass_smem = 100 * 1024;
+    p.first_pass_smem = 72 * 1024;
+    p.defer_too_large = 0;
     {
         ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);
         rc = launch_preprocess(p, (cudaStream_t)stream);

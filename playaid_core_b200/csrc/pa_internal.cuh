@@ -26,7 +26,8 @@ struct PPParams {
     int64_t plane_elems;  // distance between the hi and lo planes (PA_DTYPE_BF16X2)
     int32_t* status;
     int smem_bytes;
-    int first_pass_smem;  // > 0 in the second pass: skip crops that fit in this many bytes
+    int first_pass_smem;  // > 0 in the second pass: skip slabs that fit in this many bytes
+    int defer_too_large;  // first pass: leave slabs that do not fit to the second pass
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
 

@@ -329,19 +329,43 @@ __device__ void zero_rows(const PPParams& p, int crop, int F0, int F1) {
     }
 }
 
-struct BandPlan {
-    int f0, f1;  // final rows
-    int a0, a1;  // area-output rows (may be empty)
-    int s0, s1;  // canvas rows
-    int v0, v1;  // resized rows
-    int t0, t1;  // raw rows
+// ------------------------------------------------------------------------------------------------
+// Streaming kernel: one CTA per (crop, slab of final rows). Raw rows are pulled through three ring
+// stages entirely in shared memory -- RAW batch -> T (after the horizontal bicubic pass) ->
+// S (canvas rows after the vertical pass, with the black letterbox) -> area pass -> output --
+// so every source row is fetched and filtered once per slab, whatever the crop size.
+struct PartPlan {
+    int a0, a1;            // area-output rows of this slab
+    int s_begin, s_end;    // canvas rows they touch
+    int v_begin, v_end;    // resized-image rows among those
+    int t_begin, t_end;    // raw rows those need
+    int RB, CT, CS;        // raw rows per batch, ring capacities (rows)
+    int ok;                // 0: does not fit in shared memory
 };
+
+__device__ __forceinline__ uint32_t clip8w(int32_t v) {
+    v >>= 22;
+    return (uint32_t)min(max(v, 0), 255);
+}
+
+// canvas-row span [lo, hi) that area-output row `a` reads
+__device__ __forceinline__ void area_rows(const CropGeom& g, int a, int& lo, int& hi) {
+    if (g.regime == REG_COPY) { lo = a; hi = a + 1; }
+    else if (g.regime == REG_FAST) { lo = a * g.isy; hi = lo + g.isy; }
+    else if (g.regime == REG_GENERAL) { area_span(a, g.sd, g.scale_y, lo, hi); }
+    else {
+        int s, b0, b1;
+        linear_coef(a, g.sd, g.scale_y, g.inv_scale_y, false, s, b0, b1);
+        lo = min(max(s, 0), g.sd - 1);
+        hi = min(max(s + 1, 0), g.sd - 1) + 1;
+    }
+    lo = max(lo, 0); hi = min(hi, g.sd);
+}
 
 __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
-    __shared__ BandPlan bp;
-    __shared__ int s_band_rows;
+    __shared__ PartPlan pl;
 
     const int crop = blockIdx.x / PP_SPLIT, part = blockIdx.x % PP_SPLIT;
     const int tid = threadIdx.x;
@@ -351,79 +375,121 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
     const int F0 = (int)((int64_t)part * out / PP_SPLIT), F1 = (int)((int64_t)(part + 1) * out / PP_SPLIT);
     if (g.status != PA_CROP_OK) {
         if (p.first_pass_smem > 0) return;  // reported by the first pass
-        if (part == 0 && tid == 0 && p.status) p.status[crop] = g.status;
+        if (tid == 0 && p.status) atomicMin(p.status + crop, g.status);
         zero_rows(p, crop, F0, F1);
         return;
     }
+    const int nw = g.nw, nh = g.nh, sd = g.sd, rw = g.rw, rh = g.rh;
+    const int nw3 = nw * 3, sd3 = sd * 3;
+    const int rawp = align16(rw * 3 + 15) + 32;          // 16-byte aligned copy incl. alignment shift + over-read pad
+    const int tp = g.hact ? align16(nw3) + 16 : rawp;    // T row pitch (raw rows themselves when there is no H pass)
+    const int sp = align16(sd3) + 16;
+    const int KSH = g.hact ? (g.h_ks <= 8 ? 8 : g.h_ks) : 0;
+    const int xcap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_x) + 2 : 0;
+    const int ycap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2;
 
-    // ---- carve shared memory: [lut][tabH][xtab][per-band tables][RAW][T][S]
+    // ---- slab plan + shared-memory budget (thread 0)
+    if (tid == 0) {
+        PartPlan q;
+        q.ok = 1;
+        q.a0 = max(F0 - g.oy2, 0); q.a1 = min(F1 - g.oy2, g.oh);
+        if (q.a1 < q.a0) q.a1 = q.a0;
+        q.s_begin = q.s_end = q.v_begin = q.v_end = q.t_begin = q.t_end = 0;
+        q.RB = q.CT = q.CS = 0;
+        if (q.a1 > q.a0) {
+            int lo, hi;
+            area_rows(g, q.a0, lo, hi); q.s_begin = lo;
+            area_rows(g, q.a1 - 1, lo, hi); q.s_end = hi;
+            q.v_begin = min(max(q.s_begin - g.oy, 0), nh); q.v_end = min(max(q.s_end - g.oy, 0), nh);
+            if (q.v_end > q.v_begin) {
+                if (g.vact) {
+                    double c0 = 0.0 + (q.v_begin + 0.5) * g.v_scale;
+                    int ymin = (int)(c0 - g.v_sup + 0.5); if (ymin < 0) ymin = 0;
+                    double c1 = 0.0 + ((q.v_end - 1) + 0.5) * g.v_scale;
+                    int ymax = (int)(c1 + g.v_sup + 0.5); if (ymax > rh) ymax = rh;
+                    q.t_begin = ymin; q.t_end = ymax;
+                } else { q.t_begin = q.v_begin; q.t_end = q.v_end; }
+            }
+            // fixed tables
+            const int na = q.a1 - q.a0, nv = q.v_end - q.v_begin;
+            int fixed = 768 * 4;
+            if (g.hact) fixed += nw * 8 + nw * KSH * 4;
+            if (g.regime == REG_GENERAL) fixed += (out + 1) * 4 + out * xcap * 8;
+            else if (g.regime == REG_LINEAR) fixed += out * 4 + align16(out * 4);
+            fixed += (na + 1) * 4 + na * ycap * 8;
+            if (g.vact) fixed += nv * 8 + nv * g.v_ks * 4;
+            fixed = align16(fixed) + 64;
+            const int vwin = g.vact ? g.v_ks : 1;
+            const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)ceil(g.scale_y) + 2 : 2));
+            auto fit = [&](int limit, int& RBo, int& CTo, int& CSo) {
+                for (int RB = 32; RB >= 1; RB >>= 1) {
+                    const int CT = RB + max(vwin, g.pad1 ? 0 : awin) + 1;
+                    const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 2 : RB;
+                    const int CS = pr + awin + 1;
+                    int need = fixed + CT * tp + 64;
+                    if (g.hact) need += RB * rawp + 64;
+                    if (g.pad1) need += CS * sp;
+                    if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; return true; }
+                }
+                return false;
+            };
+            int rb, ct, cs;
+            if (p.first_pass_smem > 0 && fit(p.first_pass_smem, rb, ct, cs)) q.ok = -1;   // done by the first pass
+            else q.ok = fit(p.smem_bytes, q.RB, q.CT, q.CS) ? 1 : 0;
+        } else if (p.first_pass_smem > 0) {
+            q.ok = -1;
+        }
+        pl = q;
+    }
+    __syncthreads();
+    if (pl.ok < 0) return;
+    if (!pl.ok) {
+        if (p.defer_too_large) return;  // the second pass retries this slab with the full carve-out
+        if (tid == 0 && p.status) atomicMin(p.status + crop, PA_CROP_TOO_LARGE);
+        zero_rows(p, crop, F0, F1);
+        return;
+    }
+    if (tid == 0 && p.status) atomicMin(p.status + crop, PA_CROP_OK);  // status = worst outcome over the slabs
+    const PartPlan P = pl;
+    const int na = P.a1 - P.a0, nv = P.v_end - P.v_begin;
+
+    // ---- carve shared memory
     int off = 0;
     float* lut = (float*)(smem + off); off += 768 * 4;
-    // H-pass table: per output column xmin, n, ks coefficients
-    const int nw = g.nw, nh = g.nh, sd = g.sd, rw = g.rw, rh = g.rh;
     int* h_xmin = nullptr; int* h_n = nullptr; int32_t* h_kk = nullptr;
     if (g.hact) {
         h_xmin = (int*)(smem + off); off += nw * 4;
         h_n = (int*)(smem + off); off += nw * 4;
-        h_kk = (int32_t*)(smem + off); off += nw * g.h_ks * 4;
+        off = align16(off);
+        h_kk = (int32_t*)(smem + off); off += nw * KSH * 4;
     }
-    // area x tables
-    int xcap = 0;
-    int* xt_start = nullptr; int* xt_si = nullptr; float* xt_al = nullptr;
-    int* lx_s = nullptr; short* lx_a = nullptr;
+    int* xt_n = nullptr; int* xt_si = nullptr; float* xt_al = nullptr; int* lx_s = nullptr; short* lx_a = nullptr;
     if (g.regime == REG_GENERAL) {
-        xcap = (int)ceil(g.scale_x) + 2;
-        xt_start = (int*)(smem + off); off += (out + 1) * 4;
+        xt_n = (int*)(smem + off); off += (out + 1) * 4;
         xt_si = (int*)(smem + off); off += out * xcap * 4;
         xt_al = (float*)(smem + off); off += out * xcap * 4;
     } else if (g.regime == REG_LINEAR) {
         lx_s = (int*)(smem + off); off += out * 4;
-        lx_a = (short*)(smem + off); off += align16(out * 2 * 2);
+        lx_a = (short*)(smem + off); off += align16(out * 4);
+    }
+    int* yt_n = (int*)(smem + off); off += (na + 1) * 4;
+    int* yt_s = (int*)(smem + off); off += na * ycap * 4;
+    float* yt_b = (float*)(smem + off); off += na * ycap * 4;
+    int* v_ymin = nullptr; int* v_n = nullptr; int32_t* v_kk = nullptr;
+    if (g.vact) {
+        v_ymin = (int*)(smem + off); off += nv * 4;
+        v_n = (int*)(smem + off); off += nv * 4;
+        v_kk = (int32_t*)(smem + off); off += nv * g.v_ks * 4;
     }
     off = align16(off);
+    uint8_t* RAW = nullptr;
+    if (g.hact) { RAW = smem + off; off += P.RB * rawp + 64; }
+    uint8_t* T = smem + off; off += P.CT * tp + 64;
+    uint8_t* S = nullptr;
+    if (g.pad1) { S = smem + off; off += P.CS * sp; }
+    if (off > p.smem_bytes) { __trap(); }  // budget computed above must hold: fail loudly
 
-    // ---- band sizing
-    const int rawp = align16(rw * 3 + 15) + 16;  // aligned copy incl. alignment shift
-    const int nw3 = nw * 3, sd3 = sd * 3;
-    const int tp = align16(nw3), sp = align16(sd3);
-    const int ycap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2;
-    if (tid == 0) {
-        // largest band (final rows per pass) whose staging fits in `limit` bytes of shared memory
-        auto fit = [&](int limit) {
-            int B = F1 - F0;
-            for (; B >= 1; B = (B > 1 ? (B + 1) / 2 : 0)) {
-                int ns, nt;  // upper bounds of canvas / raw rows needed for B final rows
-                if (g.regime == REG_COPY) ns = B;
-                else if (g.regime == REG_FAST) ns = B * g.isy;
-                else ns = (int)ceil(B * g.scale_y) + 2;
-                if (ns > sd) ns = sd;
-                nt = ns;
-                if (g.vact) nt = (int)ceil(ns * g.v_scale) + 2 * (int)ceil(g.v_sup) + 2;
-                if (nt > rh) nt = rh;
-                int need = off + B * (2 + ycap * 2) * 4 + 64;  // y tables
-                if (g.vact) need += ns * (2 + g.v_ks) * 4;      // V tables
-                need += nt * rawp;                              // RAW
-                if (g.hact) need += nt * tp;                    // T
-                if (g.pad1) need += ns * sp;                    // S
-                if (need <= limit) return B;
-                if (B == 1) break;
-            }
-            return 0;
-        };
-        // second pass (whole 227 KB carve-out): only crops the first pass could not stage
-        if (p.first_pass_smem > 0 && fit(p.first_pass_smem) > 0) s_band_rows = -1;
-        else s_band_rows = fit(p.smem_bytes);
-    }
-    __syncthreads();
-    const int B = s_band_rows;
-    if (B < 0) return;  // already produced by the first pass
-    if (B == 0) {  // does not fit in shared memory even one output row at a time
-        if (part == 0 && tid == 0 && p.status) p.status[crop] = PA_CROP_TOO_LARGE;
-        zero_rows(p, crop, F0, F1);
-        return;
-    }
-    if (part == 0 && tid == 0 && p.status) p.status[crop] = PA_CROP_OK;
-    // ---- per-CTA tables
+    // ---- tables
     for (int i = tid; i < 768; i += PP_THREADS) {
         int c = i >> 8, v = i & 255;
         float f = __fdiv_rn((float)v, 255.0f);
@@ -432,14 +498,19 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
     if (g.hact) {
         for (int xx = tid; xx < nw; xx += PP_THREADS) {
             int xm, n;
-            bicubic_coeffs(xx, rw, g.h_scale, g.h_fs, g.h_sup, g.h_ks, xm, n, h_kk + (size_t)xx * g.h_ks);
+            bicubic_coeffs(xx, rw, g.h_scale, g.h_fs, g.h_sup, g.h_ks, xm, n, h_kk + (size_t)xx * KSH);
+            for (int j = g.h_ks; j < KSH; j++) h_kk[(size_t)xx * KSH + j] = 0;
             h_xmin[xx] = xm; h_n[xx] = n;
         }
     }
     if (g.regime == REG_GENERAL) {
         for (int dx = tid; dx < out; dx += PP_THREADS) {
             int n = area_entries(dx, sd, g.scale_x, xt_si + dx * xcap, xt_al + dx * xcap, xcap);
-            xt_start[dx] = n < xcap ? n : xcap;
+            xt_n[dx] = n < xcap ? n : xcap;
+        }
+        for (int i = tid; i < na; i += PP_THREADS) {
+            int n = area_entries(P.a0 + i, sd, g.scale_y, yt_s + i * ycap, yt_b + i * ycap, ycap);
+            yt_n[i] = n < ycap ? n : ycap;
         }
     } else if (g.regime == REG_LINEAR) {
         for (int dx = tid; dx < out; dx += PP_THREADS) {
@@ -447,243 +518,306 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
             linear_coef(dx, sd, g.scale_x, g.inv_scale_x, true, s, a0, a1);
             lx_s[dx] = s; lx_a[dx * 2] = (short)a0; lx_a[dx * 2 + 1] = (short)a1;
         }
+        for (int i = tid; i < na; i += PP_THREADS) {
+            int s, b0, b1;
+            linear_coef(P.a0 + i, sd, g.scale_y, g.inv_scale_y, false, s, b0, b1);
+            yt_s[i * 2] = s;
+            ((int*)yt_b)[i * 2] = b0; ((int*)yt_b)[i * 2 + 1] = b1;
+        }
+    }
+    if (g.vact) {
+        for (int i = tid; i < nv; i += PP_THREADS) {
+            int ym, n;
+            bicubic_coeffs(P.v_begin + i, rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
+            v_ymin[i] = ym; v_n[i] = n;
+        }
+    }
+    // final rows of this slab that lie in the output letterbox are black
+    for (int i = tid; i < (F1 - F0) * out; i += PP_THREADS) {
+        const int f = F0 + i / out, dx = i % out;
+        const int dy = f - g.oy2;
+        if (dy < 0 || dy >= g.oh) store_pixel(p, lut, crop, f, dx, 0, 0, 0);
     }
     __syncthreads();
+    if (na <= 0) return;
 
     const uint8_t* fbase = p.frames + (int64_t)g.frame * p.fstride;
-    const bool vec_ok = ((p.pitch & 15) == 0) && ((((uintptr_t)fbase) & 15) == 0);
+    const int64_t row0 = (int64_t)g.y0 * p.pitch + (int64_t)g.x0 * 3;
+    const bool vec_ok = ((p.pitch & 15) == 0) && ((((uintptr_t)p.frames + (uintptr_t)((int64_t)g.frame * p.fstride)) & 15) == 0);
+    const int shift = vec_ok ? (int)(row0 & 15) : 0;   // byte offset of the window inside the aligned copy
+    const int chunks = (shift + rw * 3 + 15) >> 4;
+    const bool h_fast = g.hact && (g.h_ks <= 8);
+    const uint32_t nw_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nw, 1)) + 1u;
+    const int nww = (nw3 + 3) >> 2;                      // words per T row (fast V path)
+    const uint32_t nww_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nww, 1)) + 1u;
+    const int t_off = g.hact ? 0 : shift;                // byte offset of pixel 0 in a T row
+    // canvas the area pass reads: S ring, or the raw rows themselves when there is no letterbox stage
+    const uint8_t* CV = g.pad1 ? S : T + t_off;
+    const int CVp = g.pad1 ? sp : tp;
+    const int CVcap = g.pad1 ? P.CS : P.CT;
 
-    for (int f0 = F0; f0 < F1; f0 += B) {
-        // ---------------- plan the band (thread 0)
-        if (tid == 0) {
-            BandPlan b;
-            b.f0 = f0; b.f1 = min(f0 + B, F1);
-            b.a0 = max(b.f0 - g.oy2, 0); b.a1 = min(b.f1 - g.oy2, g.oh);
-            if (b.a1 < b.a0) b.a1 = b.a0;
-            b.s0 = b.s1 = b.v0 = b.v1 = b.t0 = b.t1 = 0;
-            if (b.a1 > b.a0) {
-                if (g.regime == REG_COPY) { b.s0 = b.a0; b.s1 = b.a1; }
-                else if (g.regime == REG_FAST) { b.s0 = b.a0 * g.isy; b.s1 = b.a1 * g.isy; }
-                else if (g.regime == REG_GENERAL) {
-                    int lo, hi, lo2, hi2;
-                    area_span(b.a0, sd, g.scale_y, lo, hi);
-                    area_span(b.a1 - 1, sd, g.scale_y, lo2, hi2);
-                    b.s0 = lo; b.s1 = hi2;
-                } else {
-                    int s, a0, a1;
-                    linear_coef(b.a0, sd, g.scale_y, g.inv_scale_y, false, s, a0, a1);
-                    b.s0 = min(max(s, 0), sd - 1);
-                    linear_coef(b.a1 - 1, sd, g.scale_y, g.inv_scale_y, false, s, a0, a1);
-                    b.s1 = min(max(s + 1, 0), sd - 1) + 1;
-                }
-                b.s0 = max(b.s0, 0); b.s1 = min(b.s1, sd);
-                b.v0 = max(b.s0 - g.oy, 0); b.v1 = min(b.s1 - g.oy, nh);
-                if (b.v1 < b.v0) b.v1 = b.v0;
-                if (b.v1 > b.v0) {
-                    if (g.vact) {
-                        double c0 = 0.0 + (b.v0 + 0.5) * g.v_scale;
-                        int ymin = (int)(c0 - g.v_sup + 0.5); if (ymin < 0) ymin = 0;
-                        double c1 = 0.0 + ((b.v1 - 1) + 0.5) * g.v_scale;
-                        int ymax = (int)(c1 + g.v_sup + 0.5); if (ymax > rh) ymax = rh;
-                        b.t0 = ymin; b.t1 = ymax;
-                    } else { b.t0 = b.v0; b.t1 = b.v1; }
-                }
-            }
-            bp = b;
-        }
-        __syncthreads();
-        const BandPlan b = bp;
-        const int ns = b.s1 - b.s0, nt = b.t1 - b.t0, nv = b.v1 - b.v0, na = b.a1 - b.a0;
+    int t_done = P.t_begin;     // raw rows [t_begin, t_done) have been through the H pass (ring T)
+    int s_done = P.s_begin;     // canvas rows [s_begin, s_done) produced (ring S)
+    int a_done = P.a0;          // area rows emitted
 
-        // ---------------- carve the band region
-        int o2 = off;
-        int* yt_n = (int*)(smem + o2); o2 += (B + 1) * 4;
-        int* yt_s = (int*)(smem + o2); o2 += B * ycap * 4;      // general: si ; linear: sy
-        float* yt_b = (float*)(smem + o2); o2 += B * ycap * 4;  // general: beta ; linear: b0,b1 as ints
-        int* v_ymin = nullptr; int* v_n = nullptr; int32_t* v_kk = nullptr;
-        if (g.vact) {
-            v_ymin = (int*)(smem + o2); o2 += max(nv, 1) * 4;
-            v_n = (int*)(smem + o2); o2 += max(nv, 1) * 4;
-            v_kk = (int32_t*)(smem + o2); o2 += max(nv, 1) * g.v_ks * 4;
-        }
-        o2 = align16(o2);
-        uint8_t* RAW = smem + o2; o2 += nt * rawp;
-        uint8_t* T = RAW;
-        if (g.hact) { T = smem + o2; o2 += nt * tp; }
-        uint8_t* S = nullptr;
-        if (g.pad1) { S = smem + o2; o2 += ns * sp; }
-        if (o2 > p.smem_bytes) { __trap(); }  // sizing bound violated: fail loudly
+    auto t_needed_from = [&](int s_next) -> int {   // lowest raw row still needed once canvas rows < s_next exist
+        int v = min(max(s_next - g.oy, P.v_begin), P.v_end);
+        if (v >= P.v_end) return P.t_end;
+        return g.vact ? v_ymin[v - P.v_begin] : v;
+    };
 
-        // ---------------- band tables
-        if (g.regime == REG_GENERAL) {
-            for (int i = tid; i < na; i += PP_THREADS) {
-                int n = area_entries(b.a0 + i, sd, g.scale_y, yt_s + i * ycap, yt_b + i * ycap, ycap);
-                yt_n[i] = n < ycap ? n : ycap;
-            }
-        } else if (g.regime == REG_LINEAR) {
-            for (int i = tid; i < na; i += PP_THREADS) {
-                int s, b0, b1;
-                linear_coef(b.a0 + i, sd, g.scale_y, g.inv_scale_y, false, s, b0, b1);
-                yt_s[i * 2] = s;
-                ((int*)yt_b)[i * 2] = b0; ((int*)yt_b)[i * 2 + 1] = b1;
-            }
-        }
-        if (g.vact) {
-            for (int i = tid; i < nv; i += PP_THREADS) {
-                int ym, n;
-                bicubic_coeffs(b.v0 + i, rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
-                v_ymin[i] = ym; v_n[i] = n;
-            }
-        }
-
-        // ---------------- load raw rows [t0, t1): 128-bit reads of the 16-byte-aligned cover
-        int shift = 0;
-        if (nt > 0 && rw > 0) {
-            const int64_t row0 = (int64_t)g.y0 * p.pitch + (int64_t)g.x0 * 3;
-            if (vec_ok) {
-                shift = (int)(row0 & 15);
-                const int chunks = (shift + rw * 3 + 15) >> 4;
-                const int total = nt * chunks;
-                for (int i = tid; i < total; i += PP_THREADS) {
-                    int r = i / chunks, c = i - r * chunks;
-                    int64_t goff = (int64_t)g.frame * p.fstride + row0 - shift + (int64_t)(b.t0 + r) * p.pitch + (int64_t)c * 16;
-                    uint4 q;
-                    if (goff + 16 <= p.frames_bytes) {
-                        q = __ldg((const uint4*)(p.frames + goff));
+    while (a_done < P.a1) {
+        // ================= 1. load a batch of raw rows, horizontal pass -> T ring
+        {
+            const int t_keep = g.pad1 ? t_needed_from(s_done) : ([&] { int lo, hi; area_rows(g, a_done, lo, hi); return lo; })();
+            int nb = min(P.RB, P.t_end - t_done);
+            nb = min(nb, P.CT - (t_done - t_keep));
+            if (nb > 0) {
+                uint8_t* dstbase = g.hact ? RAW : T;
+                const int dpitch = g.hact ? rawp : tp;
+                if (rw > 0) {
+                    if (vec_ok) {
+                        const int total = nb * chunks;
+                        for (int i = tid; i < total; i += PP_THREADS) {
+                            const int r = i / chunks, c = i - r * chunks;
+                            const int t = t_done + r;
+                            const int64_t goff = (int64_t)g.frame * p.fstride + row0 - shift + (int64_t)t * p.pitch + (int64_t)c * 16;
+                            uint4 v;
+                            if (goff + 16 <= p.frames_bytes) v = __ldg((const uint4*)(p.frames + goff));
+                            else {
+                                uint8_t tmp[16];
+                                for (int k = 0; k < 16; k++) tmp[k] = (goff + k < p.frames_bytes) ? p.frames[goff + k] : 0;
+                                v = *(uint4*)tmp;
+                            }
+                            uint8_t* d = dstbase + (size_t)(g.hact ? r : (t % P.CT)) * dpitch + c * 16;
+                            *(uint4*)d = v;
+                        }
                     } else {
-                        uint8_t tmp[16];
-                        for (int k = 0; k < 16; k++) tmp[k] = (goff + k < p.frames_bytes) ? p.frames[goff + k] : 0;
-                        q = *(uint4*)tmp;
+                        const int total = nb * rw * 3;
+                        for (int i = tid; i < total; i += PP_THREADS) {
+                            const int r = i / (rw * 3), c = i - r * (rw * 3);
+                            const int t = t_done + r;
+                            dstbase[(size_t)(g.hact ? r : (t % P.CT)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
+                        }
                     }
-                    *(uint4*)(RAW + (size_t)r * rawp + c * 16) = q;
                 }
-            } else {
-                const int total = nt * rw * 3;
-                for (int i = tid; i < total; i += PP_THREADS) {
-                    int r = i / (rw * 3), c = i - r * (rw * 3);
-                    RAW[(size_t)r * rawp + c] = fbase[row0 + (int64_t)(b.t0 + r) * p.pitch + c];
+                if (g.hact) {
+                    __syncthreads();
+                    const int total = nb * nw;
+                    if (h_fast) {
+                        for (int i = tid; i < total; i += PP_THREADS) {
+                            const int r = nw > 1 ? (int)__umulhi((uint32_t)i, nw_magic) : i;
+                            const int xx = i - r * nw;
+                            const int4 ka = *(const int4*)(h_kk + (size_t)xx * 8);
+                            const int4 kb = *(const int4*)(h_kk + (size_t)xx * 8 + 4);
+                            const int k[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+                            const int boff = shift + h_xmin[xx] * 3;
+                            const uint32_t* wp = (const uint32_t*)(RAW + (size_t)r * rawp + (boff & ~3));
+                            const int sh = (boff & 3) * 8;
+                            uint32_t w[7];
+#pragma unroll
+                            for (int q = 0; q < 7; q++) w[q] = wp[q];
+                            uint32_t b[6];
+#pragma unroll
+                            for (int q = 0; q < 6; q++) b[q] = __funnelshift_r(w[q], w[q + 1], sh);
+                            int32_t s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int e = 3 * j;  // byte index of channel 0 of tap j
+                                s0 += (int)((b[e >> 2] >> ((e & 3) * 8)) & 0xFF) * k[j];
+                                s1 += (int)((b[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF) * k[j];
+                                s2 += (int)((b[(e + 2) >> 2] >> (((e + 2) & 3) * 8)) & 0xFF) * k[j];
+                            }
+                            uint8_t* d = T + (size_t)((t_done + r) % P.CT) * tp + xx * 3;
+                            d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
+                        }
+                    } else {
+                        for (int i = tid; i < total; i += PP_THREADS) {
+                            const int r = i / nw, xx = i - r * nw;
+                            const uint8_t* src = RAW + (size_t)r * rawp + shift + h_xmin[xx] * 3;
+                            const int32_t* k = h_kk + (size_t)xx * KSH;
+                            const int n = h_n[xx];
+                            int32_t s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+                            for (int j = 0; j < n; j++) {
+                                const int32_t kj = k[j];
+                                s0 += src[j * 3] * kj; s1 += src[j * 3 + 1] * kj; s2 += src[j * 3 + 2] * kj;
+                            }
+                            uint8_t* d = T + (size_t)((t_done + r) % P.CT) * tp + xx * 3;
+                            d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
+                        }
+                    }
                 }
+                t_done += nb;
             }
-        }
-        if (g.pad1) {
-            for (int i = tid * 16; i < ns * sp; i += PP_THREADS * 16) *(uint4*)(S + i) = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
 
-        // ---------------- horizontal bicubic: RAW -> T
-        if (g.hact) {
-            const int total = nt * nw;
-            for (int i = tid; i < total; i += PP_THREADS) {
-                int r = i / nw, xx = i - r * nw;
-                const uint8_t* src = RAW + (size_t)r * rawp + shift + h_xmin[xx] * 3;
-                const int32_t* k = h_kk + (size_t)xx * g.h_ks;
-                const int n = h_n[xx];
-                int32_t s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
-                for (int j = 0; j < n; j++) {
-                    int32_t kj = k[j];
-                    s0 += src[j * 3] * kj; s1 += src[j * 3 + 1] * kj; s2 += src[j * 3 + 2] * kj;
-                }
-                uint8_t* d = T + (size_t)r * tp + xx * 3;
-                d[0] = clip8_fix(s0); d[1] = clip8_fix(s1); d[2] = clip8_fix(s2);
-            }
-            __syncthreads();
-        }
-        const uint8_t* Tsrc = g.hact ? T : RAW + shift;
-        const int Tp = g.hact ? tp : rawp;
-
-        // ---------------- vertical bicubic (or copy): T -> S canvas rows
+        // ================= 2. vertical pass: canvas rows whose taps are all in T -> S ring
         if (g.pad1) {
-            const int total = nv * nw3;
-            for (int i = tid; i < total; i += PP_THREADS) {
-                int r = i / nw3, x = i - r * nw3;
-                uint8_t val;
-                if (g.vact) {
-                    const int32_t* k = v_kk + (size_t)r * g.v_ks;
-                    const int n = v_n[r];
-                    const uint8_t* src = Tsrc + (size_t)(v_ymin[r] - b.t0) * Tp + x;
-                    int32_t s = 1 << 21;
-                    for (int j = 0; j < n; j++) s += src[(size_t)j * Tp] * k[j];
-                    val = clip8_fix(s);
-                } else {
-                    val = Tsrc[(size_t)(b.v0 + r - b.t0) * Tp + x];
+            int lo_keep, hi_tmp;
+            area_rows(g, a_done, lo_keep, hi_tmp);          // lowest canvas row still needed
+            int s_new = s_done;
+            while (s_new < P.s_end && (s_new - lo_keep) < P.CS) {
+                const int v = s_new - g.oy;
+                if (v >= 0 && v < nh) {
+                    const int need = g.vact ? (v_ymin[v - P.v_begin] + v_n[v - P.v_begin]) : (v + 1);
+                    if (need > t_done) break;
                 }
-                S[(size_t)(b.v0 + r + g.oy - b.s0) * sp + g.ox * 3 + x] = val;
+                s_new++;
+            }
+            const int ns = s_new - s_done;
+            if (ns > 0) {
+                // (a) black rows and letterbox borders
+                const int lb = g.ox * 3, rb = g.ox * 3 + nw3;   // data occupies [lb, rb) of an image row
+                for (int i = tid; i < ns * (sp >> 2); i += PP_THREADS) {
+                    const int r = i / (sp >> 2), wc = i - r * (sp >> 2);
+                    const int s = s_done + r, v = s - g.oy;
+                    uint32_t* d = (uint32_t*)(S + (size_t)(s % P.CS) * sp) + wc;
+                    if (v < 0 || v >= nh) *d = 0;
+                    else if (wc * 4 + 4 <= lb || wc * 4 >= rb) *d = 0;
+                    else if (wc * 4 < lb || wc * 4 + 4 > rb) {    // word straddles a border: zero only the border bytes
+                        uint8_t* db = (uint8_t*)d;
+                        for (int q = 0; q < 4; q++) if (wc * 4 + q < lb || wc * 4 + q >= rb) db[q] = 0;
+                    }
+                }
+                // (b) image rows
+                if (g.hact) {       // T rows are word-aligned: 4 bytes per item
+                    const bool aligned_dst = ((lb & 3) == 0);
+                    const int total = ns * nww;
+                    for (int i = tid; i < total; i += PP_THREADS) {
+                        const int r = nww > 1 ? (int)__umulhi((uint32_t)i, nww_magic) : i;
+                        const int wc = i - r * nww;
+                        const int s = s_done + r, v = s - g.oy;
+                        if (v < 0 || v >= nh) continue;
+                        uint32_t o;
+                        if (g.vact) {
+                            const int vi = v - P.v_begin;
+                            const int32_t* k = v_kk + (size_t)vi * g.v_ks;
+                            const int n = v_n[vi];
+                            int slot = v_ymin[vi] % P.CT;
+                            int32_t c0 = 1 << 21, c1 = 1 << 21, c2 = 1 << 21, c3 = 1 << 21;
+                            for (int j = 0; j < n; j++) {
+                                const uint32_t w = *((const uint32_t*)(T + (size_t)slot * tp) + wc);
+                                const int32_t kj = k[j];
+                                c0 += (int)(w & 0xFF) * kj; c1 += (int)((w >> 8) & 0xFF) * kj;
+                                c2 += (int)((w >> 16) & 0xFF) * kj; c3 += (int)(w >> 24) * kj;
+                                if (++slot == P.CT) slot = 0;
+                            }
+                            o = clip8w(c0) | (clip8w(c1) << 8) | (clip8w(c2) << 16) | (clip8w(c3) << 24);
+                        } else {
+                            o = *((const uint32_t*)(T + (size_t)(v % P.CT) * tp) + wc);
+                        }
+                        uint8_t* drow = S + (size_t)(s % P.CS) * sp + lb;
+                        if (aligned_dst && wc * 4 + 4 <= nw3) *((uint32_t*)drow + wc) = o;
+                        else {
+                            for (int q = 0; q < 4; q++) if (wc * 4 + q < nw3) drow[wc * 4 + q] = (uint8_t)(o >> (8 * q));
+                        }
+                    }
+                } else {            // no H pass: T holds raw rows at byte offset t_off
+                    const int total = ns * nw3;
+                    for (int i = tid; i < total; i += PP_THREADS) {
+                        const int r = i / nw3, x = i - r * nw3;
+                        const int s = s_done + r, v = s - g.oy;
+                        if (v < 0 || v >= nh) continue;
+                        uint8_t val;
+                        if (g.vact) {
+                            const int vi = v - P.v_begin;
+                            const int32_t* k = v_kk + (size_t)vi * g.v_ks;
+                            const int n = v_n[vi];
+                            int slot = v_ymin[vi] % P.CT;
+                            int32_t c = 1 << 21;
+                            for (int j = 0; j < n; j++) {
+                                c += T[(size_t)slot * tp + t_off + x] * k[j];
+                                if (++slot == P.CT) slot = 0;
+                            }
+                            val = (uint8_t)clip8w(c);
+                        } else {
+                            val = T[(size_t)(v % P.CT) * tp + t_off + x];
+                        }
+                        S[(size_t)(s % P.CS) * sp + lb + x] = val;
+                    }
+                }
+                s_done = s_new;
             }
             __syncthreads();
         }
-        const uint8_t* CV = g.pad1 ? S : RAW + shift;  // canvas rows [s0, s1), row stride CVp
-        const int CVp = g.pad1 ? sp : rawp;
-        const int cv0 = g.pad1 ? b.s0 : b.t0;
+        const int cv_done = g.pad1 ? s_done : t_done;
 
-        // ---------------- area pass + store, one thread per final pixel
-        const int npix = (b.f1 - b.f0) * out;
+        // ================= 3. area pass for every output row whose canvas rows are ready
+        int a_new = a_done;
+        while (a_new < P.a1) {
+            int lo, hi;
+            area_rows(g, a_new, lo, hi);
+            if (hi > cv_done) break;
+            a_new++;
+        }
+        const int npix = (a_new - a_done) * out;
         for (int i = tid; i < npix; i += PP_THREADS) {
-            const int fr = i / out, dx = i - fr * out;
-            const int f = b.f0 + fr;
-            const int dy = f - g.oy2;
-            int v0 = 0, v1 = 0, v2 = 0;  // letterbox rows are black
-            if (dy >= 0 && dy < g.oh) {
-                const int ai = dy - b.a0;
-                if (g.regime == REG_COPY) {
-                    const uint8_t* q = CV + (size_t)(dy - cv0) * CVp + dx * 3;
-                    v0 = q[0]; v1 = q[1]; v2 = q[2];
-                } else if (g.regime == REG_FAST) {
-                    int a0 = 0, a1 = 0, a2 = 0;
-                    for (int sy = 0; sy < g.isy; sy++) {
-                        const uint8_t* q = CV + (size_t)(dy * g.isy + sy - cv0) * CVp + (size_t)dx * g.isx * 3;
-                        for (int sx = 0; sx < g.isx; sx++) { a0 += q[sx * 3]; a1 += q[sx * 3 + 1]; a2 += q[sx * 3 + 2]; }
-                    }
-                    if (g.isx == 2 && g.isy == 2) { v0 = (a0 + 2) >> 2; v1 = (a1 + 2) >> 2; v2 = (a2 + 2) >> 2; }
-                    else {
-                        float sc = __fdiv_rn(1.f, (float)(g.isx * g.isy));
-                        v0 = sat_u8f(__fmul_rn((float)a0, sc)); v1 = sat_u8f(__fmul_rn((float)a1, sc)); v2 = sat_u8f(__fmul_rn((float)a2, sc));
-                    }
-                } else if (g.regime == REG_GENERAL) {
-                    const int nx = xt_start[dx];
-                    const int* xsi = xt_si + dx * xcap;
-                    const float* xal = xt_al + dx * xcap;
-                    const int ny = yt_n[ai];
-                    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
-                    for (int j = 0; j < ny; j++) {
-                        const float beta = yt_b[ai * ycap + j];
-                        const uint8_t* row = CV + (size_t)(yt_s[ai * ycap + j] - cv0) * CVp;
-                        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-                        for (int k = 0; k < nx; k++) {
-                            const uint8_t* q = row + xsi[k] * 3;
-                            const float al = xal[k];
-                            b0 = __fadd_rn(b0, __fmul_rn((float)q[0], al));
-                            b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
-                            b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
-                        }
-                        if (j == 0) { m0 = __fmul_rn(beta, b0); m1 = __fmul_rn(beta, b1); m2 = __fmul_rn(beta, b2); }
-                        else {
-                            m0 = __fadd_rn(m0, __fmul_rn(beta, b0)); m1 = __fadd_rn(m1, __fmul_rn(beta, b1)); m2 = __fadd_rn(m2, __fmul_rn(beta, b2));
-                        }
-                    }
-                    v0 = sat_u8f(m0); v1 = sat_u8f(m1); v2 = sat_u8f(m2);
-                } else {  // REG_LINEAR
-                    const int sx = lx_s[dx];
-                    const int sx1 = sx + 1 < sd ? sx + 1 : sx;
-                    const int a0 = lx_a[dx * 2], a1 = lx_a[dx * 2 + 1];
-                    const int sy = yt_s[ai * 2];
-                    const int b0 = ((int*)yt_b)[ai * 2], b1 = ((int*)yt_b)[ai * 2 + 1];
-                    int r[2][3];
-                    for (int k = 0; k < 2; k++) {
-                        int yy = sy + k;
-                        yy = yy >= 0 ? (yy < sd ? yy : sd - 1) : 0;
-                        const uint8_t* row = CV + (size_t)(yy - cv0) * CVp;
-                        for (int c = 0; c < 3; c++) r[k][c] = row[sx * 3 + c] * a0 + row[sx1 * 3 + c] * a1;
-                    }
-                    int vv[3];
-                    for (int c = 0; c < 3; c++) {
-                        int t = (((b0 * (r[0][c] >> 4)) >> 16) + ((b1 * (r[1][c] >> 4)) >> 16) + 2) >> 2;
-                        vv[c] = t < 0 ? 0 : (t > 255 ? 255 : t);
-                    }
-                    v0 = vv[0]; v1 = vv[1]; v2 = vv[2];
+            const int ar = i / out, dx = i - ar * out;
+            const int dy = a_done + ar;
+            const int f = dy + g.oy2;
+            const int ai = dy - P.a0;
+            int v0, v1, v2;
+            if (g.regime == REG_COPY) {
+                const uint8_t* q = CV + (size_t)(dy % CVcap) * CVp + dx * 3;
+                v0 = q[0]; v1 = q[1]; v2 = q[2];
+            } else if (g.regime == REG_FAST) {
+                int a0 = 0, a1 = 0, a2 = 0;
+                for (int sy = 0; sy < g.isy; sy++) {
+                    const uint8_t* q = CV + (size_t)((dy * g.isy + sy) % CVcap) * CVp + (size_t)dx * g.isx * 3;
+                    for (int sx = 0; sx < g.isx; sx++) { a0 += q[sx * 3]; a1 += q[sx * 3 + 1]; a2 += q[sx * 3 + 2]; }
                 }
+                if (g.isx == 2 && g.isy == 2) { v0 = (a0 + 2) >> 2; v1 = (a1 + 2) >> 2; v2 = (a2 + 2) >> 2; }
+                else {
+                    const float sc = __fdiv_rn(1.f, (float)(g.isx * g.isy));
+                    v0 = sat_u8f(__fmul_rn((float)a0, sc)); v1 = sat_u8f(__fmul_rn((float)a1, sc)); v2 = sat_u8f(__fmul_rn((float)a2, sc));
+                }
+            } else if (g.regime == REG_GENERAL) {
+                const int nx = xt_n[dx];
+                const int* xsi = xt_si + dx * xcap;
+                const float* xal = xt_al + dx * xcap;
+                const int ny = yt_n[ai];
+                float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+                for (int j = 0; j < ny; j++) {
+                    const float beta = yt_b[ai * ycap + j];
+                    const uint8_t* row = CV + (size_t)(yt_s[ai * ycap + j] % CVcap) * CVp;
+                    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                    for (int k = 0; k < nx; k++) {
+                        const uint8_t* q = row + xsi[k] * 3;
+                        const float al = xal[k];
+                        b0 = __fadd_rn(b0, __fmul_rn((float)q[0], al));
+                        b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
+                        b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
+                    }
+                    if (j == 0) { m0 = __fmul_rn(beta, b0); m1 = __fmul_rn(beta, b1); m2 = __fmul_rn(beta, b2); }
+                    else {
+                        m0 = __fadd_rn(m0, __fmul_rn(beta, b0)); m1 = __fadd_rn(m1, __fmul_rn(beta, b1)); m2 = __fadd_rn(m2, __fmul_rn(beta, b2));
+                    }
+                }
+                v0 = sat_u8f(m0); v1 = sat_u8f(m1); v2 = sat_u8f(m2);
+            } else {  // REG_LINEAR
+                const int sx = lx_s[dx];
+                const int sx1 = sx + 1 < sd ? sx + 1 : sx;
+                const int a0 = lx_a[dx * 2], a1 = lx_a[dx * 2 + 1];
+                const int sy = yt_s[ai * 2];
+                const int b0 = ((int*)yt_b)[ai * 2], b1 = ((int*)yt_b)[ai * 2 + 1];
+                int r[2][3];
+                for (int k = 0; k < 2; k++) {
+                    int yy = sy + k;
+                    yy = yy >= 0 ? (yy < sd ? yy : sd - 1) : 0;
+                    const uint8_t* row = CV + (size_t)(yy % CVcap) * CVp;
+                    for (int c = 0; c < 3; c++) r[k][c] = row[sx * 3 + c] * a0 + row[sx1 * 3 + c] * a1;
+                }
+                int vv[3];
+                for (int c = 0; c < 3; c++) {
+                    int t = (((b0 * (r[0][c] >> 4)) >> 16) + ((b1 * (r[1][c] >> 4)) >> 16) + 2) >> 2;
+                    vv[c] = t < 0 ? 0 : (t > 255 ? 255 : t);
+                }
+                v0 = vv[0]; v1 = vv[1]; v2 = vv[2];
             }
             store_pixel(p, lut, crop, f, dx, v0, v1, v2);
         }
+        a_done = a_new;
         __syncthreads();
     }
 }
