@@ -362,7 +362,7 @@ __device__ __forceinline__ void area_rows(const CropGeom& g, int a, int& lo, int
     lo = max(lo, 0); hi = min(hi, g.sd);
 }
 
-__global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p) {
+__global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
     __shared__ PartPlan pl;
@@ -422,10 +422,12 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
             const int vwin = g.vact ? g.v_ks : 1;
             const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)ceil(g.scale_y) + 2 : 2));
             auto fit = [&](int limit, int& RBo, int& CTo, int& CSo) {
+                auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
                 for (int RB = 32; RB >= 1; RB >>= 1) {
-                    const int CT = RB + max(vwin, g.pad1 ? 0 : awin) + 1;
+                    // ring capacities are powers of two so that slot = row & (cap - 1)
+                    const int CT = pow2(RB + max(vwin, g.pad1 ? 0 : awin) + 1);
                     const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 2 : RB;
-                    const int CS = pr + awin + 1;
+                    const int CS = pow2(pr + awin + 1);
                     int need = fixed + CT * tp + 64;
                     if (g.hact) need += RB * rawp + 64;
                     if (g.pad1) need += CS * sp;
@@ -550,11 +552,16 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
     const uint32_t nw_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nw, 1)) + 1u;
     const int nww = (nw3 + 3) >> 2;                      // words per T row (fast V path)
     const uint32_t nww_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nww, 1)) + 1u;
+    const uint32_t out_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(out, 2)) + 1u;
+    const uint32_t ch_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(chunks, 2)) + 1u;
+    const int spw = sp >> 2;
+    const uint32_t spw_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(spw, 2)) + 1u;
     const int t_off = g.hact ? 0 : shift;                // byte offset of pixel 0 in a T row
     // canvas the area pass reads: S ring, or the raw rows themselves when there is no letterbox stage
     const uint8_t* CV = g.pad1 ? S : T + t_off;
     const int CVp = g.pad1 ? sp : tp;
-    const int CVcap = g.pad1 ? P.CS : P.CT;
+    const int CVmask = (g.pad1 ? P.CS : P.CT) - 1;
+    const int CTm = P.CT - 1, CSm = P.CS - 1;
 
     int t_done = P.t_begin;     // raw rows [t_begin, t_done) have been through the H pass (ring T)
     int s_done = P.s_begin;     // canvas rows [s_begin, s_done) produced (ring S)
@@ -579,7 +586,8 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                     if (vec_ok) {
                         const int total = nb * chunks;
                         for (int i = tid; i < total; i += PP_THREADS) {
-                            const int r = i / chunks, c = i - r * chunks;
+                            const int r = chunks > 1 ? (int)__umulhi((uint32_t)i, ch_magic) : i;
+                            const int c = i - r * chunks;
                             const int t = t_done + r;
                             const int64_t goff = (int64_t)g.frame * p.fstride + row0 - shift + (int64_t)t * p.pitch + (int64_t)c * 16;
                             uint4 v;
@@ -589,7 +597,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                                 for (int k = 0; k < 16; k++) tmp[k] = (goff + k < p.frames_bytes) ? p.frames[goff + k] : 0;
                                 v = *(uint4*)tmp;
                             }
-                            uint8_t* d = dstbase + (size_t)(g.hact ? r : (t % P.CT)) * dpitch + c * 16;
+                            uint8_t* d = dstbase + (size_t)(g.hact ? r : (t & CTm)) * dpitch + c * 16;
                             *(uint4*)d = v;
                         }
                     } else {
@@ -597,7 +605,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                         for (int i = tid; i < total; i += PP_THREADS) {
                             const int r = i / (rw * 3), c = i - r * (rw * 3);
                             const int t = t_done + r;
-                            dstbase[(size_t)(g.hact ? r : (t % P.CT)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
+                            dstbase[(size_t)(g.hact ? r : (t & CTm)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
                         }
                     }
                 }
@@ -624,11 +632,11 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 const int e = 3 * j;  // byte index of channel 0 of tap j
-                                s0 += (int)((b[e >> 2] >> ((e & 3) * 8)) & 0xFF) * k[j];
-                                s1 += (int)((b[(e + 1) >> 2] >> (((e + 1) & 3) * 8)) & 0xFF) * k[j];
-                                s2 += (int)((b[(e + 2) >> 2] >> (((e + 2) & 3) * 8)) & 0xFF) * k[j];
+                                s0 += (int)__byte_perm(b[e >> 2], 0, 0x4440 | (e & 3)) * k[j];
+                                s1 += (int)__byte_perm(b[(e + 1) >> 2], 0, 0x4440 | ((e + 1) & 3)) * k[j];
+                                s2 += (int)__byte_perm(b[(e + 2) >> 2], 0, 0x4440 | ((e + 2) & 3)) * k[j];
                             }
-                            uint8_t* d = T + (size_t)((t_done + r) % P.CT) * tp + xx * 3;
+                            uint8_t* d = T + (size_t)((t_done + r) & CTm) * tp + xx * 3;
                             d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
                         }
                     } else {
@@ -642,7 +650,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                                 const int32_t kj = k[j];
                                 s0 += src[j * 3] * kj; s1 += src[j * 3 + 1] * kj; s2 += src[j * 3 + 2] * kj;
                             }
-                            uint8_t* d = T + (size_t)((t_done + r) % P.CT) * tp + xx * 3;
+                            uint8_t* d = T + (size_t)((t_done + r) & CTm) * tp + xx * 3;
                             d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
                         }
                     }
@@ -669,10 +677,10 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
             if (ns > 0) {
                 // (a) black rows and letterbox borders
                 const int lb = g.ox * 3, rb = g.ox * 3 + nw3;   // data occupies [lb, rb) of an image row
-                for (int i = tid; i < ns * (sp >> 2); i += PP_THREADS) {
-                    const int r = i / (sp >> 2), wc = i - r * (sp >> 2);
+                for (int i = tid; i < ns * spw; i += PP_THREADS) {
+                    const int r = (int)__umulhi((uint32_t)i, spw_magic), wc = i - r * spw;
                     const int s = s_done + r, v = s - g.oy;
-                    uint32_t* d = (uint32_t*)(S + (size_t)(s % P.CS) * sp) + wc;
+                    uint32_t* d = (uint32_t*)(S + (size_t)(s & CSm) * sp) + wc;
                     if (v < 0 || v >= nh) *d = 0;
                     else if (wc * 4 + 4 <= lb || wc * 4 >= rb) *d = 0;
                     else if (wc * 4 < lb || wc * 4 + 4 > rb) {    // word straddles a border: zero only the border bytes
@@ -694,20 +702,20 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                             const int vi = v - P.v_begin;
                             const int32_t* k = v_kk + (size_t)vi * g.v_ks;
                             const int n = v_n[vi];
-                            int slot = v_ymin[vi] % P.CT;
+                            int slot = v_ymin[vi] & CTm;
                             int32_t c0 = 1 << 21, c1 = 1 << 21, c2 = 1 << 21, c3 = 1 << 21;
                             for (int j = 0; j < n; j++) {
                                 const uint32_t w = *((const uint32_t*)(T + (size_t)slot * tp) + wc);
                                 const int32_t kj = k[j];
-                                c0 += (int)(w & 0xFF) * kj; c1 += (int)((w >> 8) & 0xFF) * kj;
-                                c2 += (int)((w >> 16) & 0xFF) * kj; c3 += (int)(w >> 24) * kj;
-                                if (++slot == P.CT) slot = 0;
+                                c0 += (int)__byte_perm(w, 0, 0x4440) * kj; c1 += (int)__byte_perm(w, 0, 0x4441) * kj;
+                                c2 += (int)__byte_perm(w, 0, 0x4442) * kj; c3 += (int)(w >> 24) * kj;
+                                slot = (slot + 1) & CTm;
                             }
                             o = clip8w(c0) | (clip8w(c1) << 8) | (clip8w(c2) << 16) | (clip8w(c3) << 24);
                         } else {
-                            o = *((const uint32_t*)(T + (size_t)(v % P.CT) * tp) + wc);
+                            o = *((const uint32_t*)(T + (size_t)(v & CTm) * tp) + wc);
                         }
-                        uint8_t* drow = S + (size_t)(s % P.CS) * sp + lb;
+                        uint8_t* drow = S + (size_t)(s & CSm) * sp + lb;
                         if (aligned_dst && wc * 4 + 4 <= nw3) *((uint32_t*)drow + wc) = o;
                         else {
                             for (int q = 0; q < 4; q++) if (wc * 4 + q < nw3) drow[wc * 4 + q] = (uint8_t)(o >> (8 * q));
@@ -724,17 +732,17 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                             const int vi = v - P.v_begin;
                             const int32_t* k = v_kk + (size_t)vi * g.v_ks;
                             const int n = v_n[vi];
-                            int slot = v_ymin[vi] % P.CT;
+                            int slot = v_ymin[vi] & CTm;
                             int32_t c = 1 << 21;
                             for (int j = 0; j < n; j++) {
                                 c += T[(size_t)slot * tp + t_off + x] * k[j];
-                                if (++slot == P.CT) slot = 0;
+                                slot = (slot + 1) & CTm;
                             }
                             val = (uint8_t)clip8w(c);
                         } else {
-                            val = T[(size_t)(v % P.CT) * tp + t_off + x];
+                            val = T[(size_t)(v & CTm) * tp + t_off + x];
                         }
-                        S[(size_t)(s % P.CS) * sp + lb + x] = val;
+                        S[(size_t)(s & CSm) * sp + lb + x] = val;
                     }
                 }
                 s_done = s_new;
@@ -753,18 +761,19 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
         }
         const int npix = (a_new - a_done) * out;
         for (int i = tid; i < npix; i += PP_THREADS) {
-            const int ar = i / out, dx = i - ar * out;
+            const int ar = out > 1 ? (int)__umulhi((uint32_t)i, out_magic) : i;
+            const int dx = i - ar * out;
             const int dy = a_done + ar;
             const int f = dy + g.oy2;
             const int ai = dy - P.a0;
             int v0, v1, v2;
             if (g.regime == REG_COPY) {
-                const uint8_t* q = CV + (size_t)(dy % CVcap) * CVp + dx * 3;
+                const uint8_t* q = CV + (size_t)(dy & CVmask) * CVp + dx * 3;
                 v0 = q[0]; v1 = q[1]; v2 = q[2];
             } else if (g.regime == REG_FAST) {
                 int a0 = 0, a1 = 0, a2 = 0;
                 for (int sy = 0; sy < g.isy; sy++) {
-                    const uint8_t* q = CV + (size_t)((dy * g.isy + sy) % CVcap) * CVp + (size_t)dx * g.isx * 3;
+                    const uint8_t* q = CV + (size_t)((dy * g.isy + sy) & CVmask) * CVp + (size_t)dx * g.isx * 3;
                     for (int sx = 0; sx < g.isx; sx++) { a0 += q[sx * 3]; a1 += q[sx * 3 + 1]; a2 += q[sx * 3 + 2]; }
                 }
                 if (g.isx == 2 && g.isy == 2) { v0 = (a0 + 2) >> 2; v1 = (a1 + 2) >> 2; v2 = (a2 + 2) >> 2; }
@@ -780,7 +789,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                 float m0 = 0.f, m1 = 0.f, m2 = 0.f;
                 for (int j = 0; j < ny; j++) {
                     const float beta = yt_b[ai * ycap + j];
-                    const uint8_t* row = CV + (size_t)(yt_s[ai * ycap + j] % CVcap) * CVp;
+                    const uint8_t* row = CV + (size_t)(yt_s[ai * ycap + j] & CVmask) * CVp;
                     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
                     for (int k = 0; k < nx; k++) {
                         const uint8_t* q = row + xsi[k] * 3;
@@ -805,7 +814,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PPParams p
                 for (int k = 0; k < 2; k++) {
                     int yy = sy + k;
                     yy = yy >= 0 ? (yy < sd ? yy : sd - 1) : 0;
-                    const uint8_t* row = CV + (size_t)(yy % CVcap) * CVp;
+                    const uint8_t* row = CV + (size_t)(yy & CVmask) * CVp;
                     for (int c = 0; c < 3; c++) r[k][c] = row[sx * 3 + c] * a0 + row[sx1 * 3 + c] * a1;
                 }
                 int vv[3];
