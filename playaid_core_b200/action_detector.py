@@ -29,43 +29,58 @@ from .preprocess import crop_records, preprocess_crops
 
 
 class MatchStream:
-    """Streaming state for one match: crop records and window tables (device-resident, built once from
-    the whole log), the feature table, and how far crops / labels have progressed."""
+    """Streaming state for one match (or one rank's shard of it): crop records and window tables
+    (device-resident, built once from the log), the feature table, and how far crops / labels have
+    progressed.
 
-    def __init__(self, det: "ActionDetector", boxes: np.ndarray, H: int, W: int):
+    `boxes` holds the frames this stream will be fed, i.e. global frames
+    [frame_offset, frame_offset + len(boxes)) of a video with `total_frames` frames; labels are produced
+    for global frames [own[0], own[1]) (default: all of them). Window indices are clamped at the ends of
+    the *video*, not of the shard, so a shard with a `reach`-frame halo reproduces the single-GPU labels.
+    """
+
+    def __init__(self, det: "ActionDetector", boxes: np.ndarray, H: int, W: int, frame_offset: int = 0,
+                 total_frames: int | None = None, own: tuple[int, int] | None = None):
         self.det, self.H, self.W = det, int(H), int(W)
         self.N, self.F = int(boxes.shape[0]), int(boxes.shape[1])
+        self.offset = int(frame_offset)
+        self.total = int(total_frames) if total_frames is not None else self.offset + self.N
+        lo, hi = own if own is not None else (self.offset, self.offset + self.N)
+        lo = max(lo, det.min_frame)
+        self.own = (lo, max(hi, lo))
         self.boxes = boxes
         dev = det.model._device
         A, S = det.model.num_actions, det.num_frames_per_sample
         rec = crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(self.N), self.F), self.W, self.H)
         self.rec = torch.from_numpy(rec).to(dev)
+        n_own = self.own[1] - self.own[0]
         self.feat = torch.zeros((self.N * self.F, 1000), dtype=torch.float32, device=dev)
-        self.logp = torch.empty((self.N, self.F, A), dtype=torch.float32, device=dev)
-        self.label = torch.full((self.N, self.F), -1, dtype=torch.int32, device=dev)
-        self.prob = torch.zeros((self.N, self.F), dtype=torch.float32, device=dev)
+        self.logp = torch.empty((n_own, self.F, A), dtype=torch.float32, device=dev)
+        self.label = torch.full((n_own, self.F), -1, dtype=torch.int32, device=dev)
+        self.prob = torch.zeros((n_own, self.F), dtype=torch.float32, device=dev)
         self.status = torch.zeros((self.N, self.F), dtype=torch.int32, device=dev)
-        self.pushed = 0   # frames whose features are in the table
-        self.labeled = 0  # frames whose windows have been classified
-        # window indices of every frame, as frame numbers (host) -- dataset_utils.py:109-138
-        self.win_frames = window_index_table(np.arange(det.min_frame, self.N), S, det.frame_delta, max_frames=self.N,
-                                             min_frame=det.min_frame)
-        # ... and as feature-table rows (device): row = frame * F + fighter
-        idx = self.win_frames[:, None, :].astype(np.int64) * self.F + np.arange(self.F)[None, :, None]
-        self.win_rows = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(dev)  # [N-min, F, S]
-        mid = S // 2
-        self.reach = det.frame_delta * mid * mid
+        self.pushed = 0   # local frames whose features are in the table
+        self.labeled = 0  # own frames whose windows have been classified
+        # window indices of every own frame as LOCAL frame numbers -- dataset_utils.py:109-138
+        wf = window_index_table(np.arange(self.own[0], self.own[1]), S, det.frame_delta, max_frames=self.total,
+                                min_frame=det.min_frame) - self.offset
+        assert n_own == 0 or (wf.min() >= 0 and wf.max() < self.N), "shard lacks the halo frames its windows reach"
+        self.win_frames = wf
+        self.need = wf.max(axis=1) if n_own else np.zeros((0,), np.int64)  # last local frame each window needs
+        idx = wf[:, None, :].astype(np.int64) * self.F + np.arange(self.F)[None, :, None]
+        self.win_rows = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(dev)  # [n_own, F, S]
 
     def push(self, frames: torch.Tensor) -> tuple[int, int]:
-        """frames uint8 CUDA [n,H,W,3]: match frames [pushed, pushed+n). Returns the [a, b) range of
-        frames labelled by this call (labels trail by the window reach until the match ends)."""
+        """frames uint8 CUDA [n,H,W,3]: local frames [pushed, pushed+n). Returns the [a, b) range of own
+        frames (indices into `label`) classified by this call; labels trail the pushed frames by the
+        window reach until the last frame arrives."""
         det = self.det
         n = int(frames.shape[0])
         f0 = self.pushed
         assert f0 + n <= self.N
         rec = self.rec[f0 * self.F : (f0 + n) * self.F].clone()
         rec[:, 0] -= f0  # frame index relative to this chunk
-        crops, status = preprocess_crops(
+        crops, _ = preprocess_crops(
             frames, rec, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
             dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4, out=det._crop_buffer(n * self.F),
             status=self.status[f0 : f0 + n].view(-1),
@@ -76,13 +91,13 @@ class MatchStream:
 
     def _label_ready(self) -> tuple[int, int]:
         det = self.det
-        a = max(self.labeled, det.min_frame)
-        b = self.N if self.pushed == self.N else max(a, self.pushed - self.reach)
+        a = self.labeled
+        b = int(np.searchsorted(self.need, self.pushed - 1, side="right"))
         if b <= a:
             return (a, a)
-        wf = self.win_frames[a - det.min_frame : b - det.min_frame]
-        lo, hi = int(wf.min()), int(wf.max()) + 1  # feature rows the windows centred on [a, b) touch
-        idx = (self.win_rows[a - det.min_frame : b - det.min_frame] - lo * self.F).view(-1, wf.shape[1]).contiguous()
+        wf = self.win_frames[a:b]
+        lo, hi = int(wf.min()), int(wf.max()) + 1  # local feature frames the windows [a, b) touch
+        idx = (self.win_rows[a:b] - lo * self.F).view(-1, wf.shape[1]).contiguous()
         logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx)
         self.logp[a:b] = logp.view(b - a, self.F, -1)
         self.label[a:b] = label.view(b - a, self.F)
@@ -120,9 +135,10 @@ class ActionDetector:
             self._crops = torch.empty(shape, dtype=self.model.act_dtype, device=self.model._device)
         return self._crops
 
-    def stream(self, boxes: np.ndarray, H: int, W: int) -> MatchStream:
-        """boxes float64 [N,F,4]: every (frame, fighter) box of the match (from the ult_logger log)."""
-        return MatchStream(self, boxes, H, W)
+    def stream(self, boxes: np.ndarray, H: int, W: int, **shard) -> MatchStream:
+        """boxes float64 [N,F,4]: every (frame, fighter) box of the match (from the ult_logger log).
+        `shard` = frame_offset / total_frames / own for one rank's slice (see parallel.frame_shard)."""
+        return MatchStream(self, boxes, H, W, **shard)
 
     def classify_clip(self, frames: torch.Tensor, boxes: np.ndarray, chunk: int = 256) -> dict:
         """frames uint8 CUDA [N,H,W,3] (BGR, as decoded by cv2), boxes float64 [N,F,4] normalised.
@@ -131,6 +147,23 @@ class ActionDetector:
         st = self.stream(boxes[:N], H, W)
         for s in range(0, N, chunk):
             st.push(frames[s : s + chunk])
+        label, logp, prob = st.label, st.logp, st.prob
+        if self.min_frame > 0:  # AIRunner-style 1-indexed runs leave the frames below min_frame unlabelled
+            pad = self.min_frame
+            label = torch.cat([torch.full((pad, st.F), -1, dtype=label.dtype, device=label.device), label])
+            logp = torch.cat([torch.zeros((pad,) + tuple(logp.shape[1:]), dtype=logp.dtype, device=logp.device), logp])
+            prob = torch.cat([torch.zeros((pad, st.F), dtype=prob.dtype, device=prob.device), prob])
+        return {"label": label, "logp": logp, "prob": prob, "status": st.status}
+
+    def classify_shard(self, frames_halo: torch.Tensor, boxes_halo: np.ndarray, halo_lo: int, own: tuple[int, int],
+                       total_frames: int, chunk: int = 256) -> dict:
+        """One rank's slice of a long video: `frames_halo` / `boxes_halo` cover global frames
+        [halo_lo, halo_lo + n) (own range plus the window halo, parallel.frame_shard); labels are
+        returned for global frames [own[0], own[1])."""
+        n, H, W, _ = frames_halo.shape
+        st = self.stream(boxes_halo[:n], H, W, frame_offset=halo_lo, total_frames=total_frames, own=own)
+        for s in range(0, n, chunk):
+            st.push(frames_halo[s : s + chunk])
         return {"label": st.label, "logp": st.logp, "prob": st.prob, "status": st.status}
 
     def classify_timeline(self, frames: torch.Tensor, timeline, chunk: int = 256) -> dict:

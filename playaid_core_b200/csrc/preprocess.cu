@@ -423,15 +423,19 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)ceil(g.scale_y) + 2 : 2));
             auto fit = [&](int limit, int& RBo, int& CTo, int& CSo) {
                 auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
-                for (int RB = 32; RB >= 1; RB >>= 1) {
-                    // ring capacities are powers of two so that slot = row & (cap - 1)
-                    const int CT = pow2(RB + max(vwin, g.pad1 ? 0 : awin) + 1);
-                    const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 2 : RB;
-                    const int CS = pow2(pr + awin + 1);
-                    int need = fixed + CT * tp + 64;
-                    if (g.hact) need += RB * rawp + 64;
-                    if (g.pad1) need += CS * sp;
-                    if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; return true; }
+                // ring capacities are powers of two (slot = row & (cap - 1)); very wide windows that
+                // only fit with exact capacities take the modulo path
+                for (int exact = 0; exact < 2; exact++) {
+                    for (int RB = exact ? 4 : 32; RB >= 1; RB >>= 1) {
+                        int CT = RB + max(vwin, g.pad1 ? 0 : awin) + 1;
+                        const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 2 : RB;
+                        int CS = pr + awin + 1;
+                        if (!exact) { CT = pow2(CT); CS = pow2(CS); }
+                        int need = fixed + CT * tp + 64;
+                        if (g.hact) need += RB * rawp + 64;
+                        if (g.pad1) need += CS * sp;
+                        if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; return true; }
+                    }
                 }
                 return false;
             };
@@ -560,8 +564,11 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     // canvas the area pass reads: S ring, or the raw rows themselves when there is no letterbox stage
     const uint8_t* CV = g.pad1 ? S : T + t_off;
     const int CVp = g.pad1 ? sp : tp;
-    const int CVmask = (g.pad1 ? P.CS : P.CT) - 1;
-    const int CTm = P.CT - 1, CSm = P.CS - 1;
+    // ring slot of a row: mask when the capacity is a power of two (the usual case), modulo otherwise
+    const bool ct_p2 = (P.CT & (P.CT - 1)) == 0, cs_p2 = (P.CS & (P.CS - 1)) == 0;
+    auto slotT = [&](int row) { return ct_p2 ? (row & (P.CT - 1)) : (row % P.CT); };
+    auto slotS = [&](int row) { return cs_p2 ? (row & (P.CS - 1)) : (row % P.CS); };
+    auto slotCV = [&](int row) { return g.pad1 ? slotS(row) : slotT(row); };
 
     int t_done = P.t_begin;     // raw rows [t_begin, t_done) have been through the H pass (ring T)
     int s_done = P.s_begin;     // canvas rows [s_begin, s_done) produced (ring S)
@@ -597,7 +604,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                                 for (int k = 0; k < 16; k++) tmp[k] = (goff + k < p.frames_bytes) ? p.frames[goff + k] : 0;
                                 v = *(uint4*)tmp;
                             }
-                            uint8_t* d = dstbase + (size_t)(g.hact ? r : (t & CTm)) * dpitch + c * 16;
+                            uint8_t* d = dstbase + (size_t)(g.hact ? r : slotT(t)) * dpitch + c * 16;
                             *(uint4*)d = v;
                         }
                     } else {
@@ -605,7 +612,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                         for (int i = tid; i < total; i += PP_THREADS) {
                             const int r = i / (rw * 3), c = i - r * (rw * 3);
                             const int t = t_done + r;
-                            dstbase[(size_t)(g.hact ? r : (t & CTm)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
+                            dstbase[(size_t)(g.hact ? r : slotT(t)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
                         }
                     }
                 }
@@ -636,7 +643,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                                 s1 += (int)__byte_perm(b[(e + 1) >> 2], 0, 0x4440 | ((e + 1) & 3)) * k[j];
                                 s2 += (int)__byte_perm(b[(e + 2) >> 2], 0, 0x4440 | ((e + 2) & 3)) * k[j];
                             }
-                            uint8_t* d = T + (size_t)((t_done + r) & CTm) * tp + xx * 3;
+                            uint8_t* d = T + (size_t)slotT(t_done + r) * tp + xx * 3;
                             d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
                         }
                     } else {
@@ -650,7 +657,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                                 const int32_t kj = k[j];
                                 s0 += src[j * 3] * kj; s1 += src[j * 3 + 1] * kj; s2 += src[j * 3 + 2] * kj;
                             }
-                            uint8_t* d = T + (size_t)((t_done + r) & CTm) * tp + xx * 3;
+                            uint8_t* d = T + (size_t)slotT(t_done + r) * tp + xx * 3;
                             d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
                         }
                     }
@@ -680,7 +687,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                 for (int i = tid; i < ns * spw; i += PP_THREADS) {
                     const int r = (int)__umulhi((uint32_t)i, spw_magic), wc = i - r * spw;
                     const int s = s_done + r, v = s - g.oy;
-                    uint32_t* d = (uint32_t*)(S + (size_t)(s & CSm) * sp) + wc;
+                    uint32_t* d = (uint32_t*)(S + (size_t)slotS(s) * sp) + wc;
                     if (v < 0 || v >= nh) *d = 0;
                     else if (wc * 4 + 4 <= lb || wc * 4 >= rb) *d = 0;
                     else if (wc * 4 < lb || wc * 4 + 4 > rb) {    // word straddles a border: zero only the border bytes
@@ -702,20 +709,20 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                             const int vi = v - P.v_begin;
                             const int32_t* k = v_kk + (size_t)vi * g.v_ks;
                             const int n = v_n[vi];
-                            int slot = v_ymin[vi] & CTm;
+                            int slot = slotT(v_ymin[vi]);
                             int32_t c0 = 1 << 21, c1 = 1 << 21, c2 = 1 << 21, c3 = 1 << 21;
                             for (int j = 0; j < n; j++) {
                                 const uint32_t w = *((const uint32_t*)(T + (size_t)slot * tp) + wc);
                                 const int32_t kj = k[j];
                                 c0 += (int)__byte_perm(w, 0, 0x4440) * kj; c1 += (int)__byte_perm(w, 0, 0x4441) * kj;
                                 c2 += (int)__byte_perm(w, 0, 0x4442) * kj; c3 += (int)(w >> 24) * kj;
-                                slot = (slot + 1) & CTm;
+                                if (++slot == P.CT) slot = 0;
                             }
                             o = clip8w(c0) | (clip8w(c1) << 8) | (clip8w(c2) << 16) | (clip8w(c3) << 24);
                         } else {
-                            o = *((const uint32_t*)(T + (size_t)(v & CTm) * tp) + wc);
+                            o = *((const uint32_t*)(T + (size_t)slotT(v) * tp) + wc);
                         }
-                        uint8_t* drow = S + (size_t)(s & CSm) * sp + lb;
+                        uint8_t* drow = S + (size_t)slotS(s) * sp + lb;
                         if (aligned_dst && wc * 4 + 4 <= nw3) *((uint32_t*)drow + wc) = o;
                         else {
                             for (int q = 0; q < 4; q++) if (wc * 4 + q < nw3) drow[wc * 4 + q] = (uint8_t)(o >> (8 * q));
@@ -732,17 +739,17 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                             const int vi = v - P.v_begin;
                             const int32_t* k = v_kk + (size_t)vi * g.v_ks;
                             const int n = v_n[vi];
-                            int slot = v_ymin[vi] & CTm;
+                            int slot = slotT(v_ymin[vi]);
                             int32_t c = 1 << 21;
                             for (int j = 0; j < n; j++) {
                                 c += T[(size_t)slot * tp + t_off + x] * k[j];
-                                slot = (slot + 1) & CTm;
+                                if (++slot == P.CT) slot = 0;
                             }
                             val = (uint8_t)clip8w(c);
                         } else {
-                            val = T[(size_t)(v & CTm) * tp + t_off + x];
+                            val = T[(size_t)slotT(v) * tp + t_off + x];
                         }
-                        S[(size_t)(s & CSm) * sp + lb + x] = val;
+                        S[(size_t)slotS(s) * sp + lb + x] = val;
                     }
                 }
                 s_done = s_new;
@@ -768,12 +775,12 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             const int ai = dy - P.a0;
             int v0, v1, v2;
             if (g.regime == REG_COPY) {
-                const uint8_t* q = CV + (size_t)(dy & CVmask) * CVp + dx * 3;
+                const uint8_t* q = CV + (size_t)slotCV(dy) * CVp + dx * 3;
                 v0 = q[0]; v1 = q[1]; v2 = q[2];
             } else if (g.regime == REG_FAST) {
                 int a0 = 0, a1 = 0, a2 = 0;
                 for (int sy = 0; sy < g.isy; sy++) {
-                    const uint8_t* q = CV + (size_t)((dy * g.isy + sy) & CVmask) * CVp + (size_t)dx * g.isx * 3;
+                    const uint8_t* q = CV + (size_t)slotCV(dy * g.isy + sy) * CVp + (size_t)dx * g.isx * 3;
                     for (int sx = 0; sx < g.isx; sx++) { a0 += q[sx * 3]; a1 += q[sx * 3 + 1]; a2 += q[sx * 3 + 2]; }
                 }
                 if (g.isx == 2 && g.isy == 2) { v0 = (a0 + 2) >> 2; v1 = (a1 + 2) >> 2; v2 = (a2 + 2) >> 2; }
@@ -789,7 +796,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                 float m0 = 0.f, m1 = 0.f, m2 = 0.f;
                 for (int j = 0; j < ny; j++) {
                     const float beta = yt_b[ai * ycap + j];
-                    const uint8_t* row = CV + (size_t)(yt_s[ai * ycap + j] & CVmask) * CVp;
+                    const uint8_t* row = CV + (size_t)slotCV(yt_s[ai * ycap + j]) * CVp;
                     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
                     for (int k = 0; k < nx; k++) {
                         const uint8_t* q = row + xsi[k] * 3;
@@ -814,7 +821,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                 for (int k = 0; k < 2; k++) {
                     int yy = sy + k;
                     yy = yy >= 0 ? (yy < sd ? yy : sd - 1) : 0;
-                    const uint8_t* row = CV + (size_t)(yy & CVmask) * CVp;
+                    const uint8_t* row = CV + (size_t)slotCV(yy) * CVp;
                     for (int c = 0; c < 3; c++) r[k][c] = row[sx * 3 + c] * a0 + row[sx1 * 3 + c] * a1;
                 }
                 int vv[3];
