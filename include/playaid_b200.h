@@ -47,7 +47,9 @@ extern "C" {
 #define PA_DTYPE_F16X2 5  /* half hi plane followed by a half lo (rounding residual) plane */
 #define PA_LAYOUT_NHWC 0
 #define PA_LAYOUT_NCHW 1
-#define PA_LAYOUT_NHWC4 2 /* 4 channels per pixel, channel 3 == 0: the conv1-ready layout */
+#define PA_LAYOUT_NHWC4 2 /* 4 channels per pixel, channel 3 == 0 */
+#define PA_LAYOUT_NHWC4P 3 /* NHWC4 with 4 zero pixels left and right of every row ([n][out][out+8][4]):
+                              the conv1-ready layout (TMA im2col needs the horizontal padding in memory) */
 
 /* classifier arithmetic (pa_model_finalize) */
 #define PA_PREC_BF16 0   /* bf16 operands, fp32 accumulate: 1 tcgen05 MMA per k-step            */
@@ -115,10 +117,10 @@ int pa_model_precision(const pa_model* m);
 int pa_model_workspace_bytes(const pa_model* m, int n_crops, size_t* bytes);
 
 /*
- * ResNet-18 features, once per crop. crops: bf16 NHWC4 [n_crops][128][128][4] (channel 3 == 0)
- * as written by pa_preprocess(out_dtype=PA_DTYPE_BF16, out_layout=PA_LAYOUT_NHWC) with the
- * 4-channel pitch this library uses internally -- see pa_crop_elems(); in PA_PREC_BF16X2/X3 the
- * lo plane follows the hi plane. feat: fp32 [n_crops][1000].
+ * ResNet-18 features, once per crop. crops: 16-bit NHWC4P [n_crops][128][136][4] (channel 3 == 0, 4 zero
+ * pixels either side of a row) as written by pa_preprocess(out_layout=PA_LAYOUT_NHWC4P) with the
+ * out_dtype matching the model's precision; in split precisions the lo plane follows the hi plane.
+ * feat: fp32 [n_crops][1000].
  */
 int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace,
                 size_t workspace_bytes, void* stream);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libplayaid_b200.so")
 PA_OK = 0
 CROP_OK, CROP_INVALID, CROP_ZERO_DIV, CROP_TOO_LARGE = 1, 0, -2, -7
 DTYPE_U8, DTYPE_BF16, DTYPE_F32, DTYPE_BF16X2, DTYPE_F16, DTYPE_F16X2 = 0, 1, 2, 3, 4, 5
-LAYOUT_NHWC, LAYOUT_NCHW, LAYOUT_NHWC4 = 0, 1, 2
+LAYOUT_NHWC, LAYOUT_NCHW, LAYOUT_NHWC4, LAYOUT_NHWC4P = 0, 1, 2, 3
 PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_F16, PREC_F16X2, PREC_F16X3 = 0, 1, 2, 3, 4, 5
 BOX_STRIDE = 8
 

@@ -82,7 +82,7 @@ class MatchStream:
         rec[:, 0] -= f0  # frame index relative to this chunk
         crops, _ = preprocess_crops(
             frames, rec, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
-            dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4, out=det._crop_buffer(n * self.F),
+            dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4P, out=det._crop_buffer(n * self.F),
             status=self.status[f0 : f0 + n].view(-1),
         )
         det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
@@ -130,7 +130,7 @@ class ActionDetector:
 
     def _crop_buffer(self, n: int) -> torch.Tensor:
         planes = 2 if self.model.split else 1
-        shape = (planes, n, self.output_size, self.output_size, 4) if planes == 2 else (n, self.output_size, self.output_size, 4)
+        shape = (planes, n, self.output_size, self.output_size + 8, 4) if planes == 2 else (n, self.output_size, self.output_size + 8, 4)
         if self._crops is None or tuple(self._crops.shape) != shape or self._crops.dtype != self.model.act_dtype:
             self._crops = torch.empty(shape, dtype=self.model.act_dtype, device=self.model._device)
         return self._crops

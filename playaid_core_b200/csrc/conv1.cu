@@ -1,15 +1,18 @@
-// ResNet stem: conv 7x7 stride 2 pad 3 (3 -> 64) + folded BN + ReLU as a tcgen05 implicit GEMM.
+// ResNet stem: conv 7x7 stride 2 pad 3 (3 -> 64) + folded BN + ReLU as a tcgen05 implicit GEMM
+// whose im2col is done entirely by the TMA unit.
 //
-// Cin = 3 cannot feed a TMA im2col box, so the A tile is assembled by four producer warps:
-// the input is the 4-channel bf16 crop written by the preprocess kernel (NHWC4, channel 3 == 0);
-// for one output pixel and one filter row ky the 8 input pixels x 4 channels it touches are one
-// contiguous, 16-byte aligned 64-byte run (2*ox-4 .. 2*ox+3), so K is laid out as
-//   k = ky*32 + kx8*4 + c      (kx8 = kx + 1; weight is 0 for kx8 == 0 and for c == 3)
-// i.e. 7 filter rows x 32 = 224 = 14 tcgen05 k-steps of 16. Producers copy four 16-byte chunks per
-// (pixel, ky) into the K-major SWIZZLE_128B tile with zero fill outside the image, fence to the
-// async proxy and signal an mbarrier; one thread issues the 14 (x2 / x3 in split precision) MMAs
-// into a double-buffered TMEM accumulator; four epilogue warps apply scale/shift + ReLU and store
-// NHWC bf16 (hi [+ lo]).
+// Input: the 16-bit crop written by the preprocess kernel in NHWC4P layout -- 4 channels per pixel
+// (channel 3 == 0) and 4 zero pixels left/right of every row: [n][128][136][4]. For one output pixel
+// (oy, ox) and one filter row ky the 8 input pixels x 4 channels it touches (2ox-4 .. 2ox+3, the
+// leftmost one multiplied by a zero weight) are ONE contiguous 64-byte run starting at padded pixel
+// 2ox. So K is laid out as
+//     k = ky*32 + kx8*4 + c        (kx8 = kx + 1; weight 0 for kx8 == 0 and c == 3)
+// and the A tile of filter row ky for 128 output pixels (2 output rows x 64 columns) is a 4-D TMA box
+//     [32 elements, 64 ox (stride 16 B -- overlapping windows), 2 row-pairs (stride 2 rows), 1 crop]
+// of a tensor map over every other input row (one map per row parity); rows above/below the image
+// are zero-filled by the TMA unit, columns by the padding in memory. Seven 8 KB boxes per tile land
+// in K-major SWIZZLE_64B tiles, 14 tcgen05.mma (M=128, N=64, K=16) accumulate in TMEM
+// (double-buffered), four epilogue warps apply scale/shift + ReLU and store NHWC.
 //
 // Replaces resnet18.conv1/bn1/relu (torchvision, via playaid/models/cnn_action_detector.py:16,32).
 #include "pa_internal.cuh"
@@ -17,121 +20,106 @@
 
 namespace pa {
 
-constexpr int C1_THREADS = 288;
-constexpr int C1_A_PLANE = 4 * 16384;  // 4 k-blocks of [128 rows x 128 B]
-constexpr int C1_B_PLANE = 4 * 8192;   // 4 k-blocks of [64 rows x 128 B]
-constexpr int C1_IN = 128, C1_OUT = 64, C1_COUT = 64;
+constexpr int C1_THREADS = 192;
+constexpr int C1_A_KY = 128 * 64;          // one filter row of the A tile: 128 rows x 64 B
+constexpr int C1_A_PLANE = 7 * C1_A_KY;    // 56 KB
+constexpr int C1_B_KY = 64 * 64;           // 64 cout rows x 64 B
+constexpr int C1_B_PLANE = 7 * C1_B_KY;    // 28 KB
+constexpr int C1_COUT = 64;
 
 template <int NA, int NB>
-__global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const Conv1Args a) {
+__global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int NBUF = (NA == 1) ? 2 : 1;
-    uint8_t* sA = smem;                                  // [NBUF][NA][C1_A_PLANE]
-    uint8_t* sB = smem + NBUF * NA * C1_A_PLANE;         // [NB][C1_B_PLANE]
+    constexpr int NSTAGE = (NA == 1) ? 3 : 1;
+    constexpr int STAGE_BYTES = NA * C1_A_PLANE;
+    uint8_t* sA = smem;                                    // [NSTAGE][NA][7][128 x 64 B]
+    uint8_t* sB = smem + NSTAGE * STAGE_BYTES;             // [NB][7][64 x 64 B]
     uint64_t* bars = (uint64_t*)(sB + NB * C1_B_PLANE);
-    uint64_t* afull = bars;        // [2]
-    uint64_t* aempty = bars + 2;   // [2]
-    uint64_t* tfull = bars + 4;    // [2]
-    uint64_t* tempty = bars + 6;   // [2]
-    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    uint64_t* afull = bars;          // [NSTAGE]
+    uint64_t* aempty = bars + 3;     // [NSTAGE]
+    uint64_t* tfull = bars + 6;      // [2]
+    uint64_t* tempty = bars + 8;     // [2]
+    uint64_t* bfull = bars + 10;     // weights landed
+    uint32_t* tmem_slot = (uint32_t*)(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = a.n_crops * (C1_OUT * C1_OUT / 128);
+    const int total_tiles = a.n_crops * 32;
 
-    // weights -> smem (SWIZZLE_128B K-major), once per CTA
-    for (int pl = 0; pl < NB; pl++) {
-        const uint4* w = (const uint4*)(pl == 0 ? a.w_hi : a.w_lo);
-        for (int i = threadIdx.x; i < 64 * 32; i += C1_THREADS) {
-            const int n = i >> 5, ch = i & 31;  // 32 chunks of 16 B per row of 256 bf16
-            const int kb = ch >> 3, c = ch & 7;
-            *(uint4*)(sB + pl * C1_B_PLANE + kb * 8192 + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4)) = __ldg(w + i);
-        }
+    if (warp == 0 && lane == 0) {
+        for (int pl = 0; pl < NA; pl++) { tma_prefetch_desc(&maps.a[pl][0]); tma_prefetch_desc(&maps.a[pl][1]); }
+        for (int pl = 0; pl < NB; pl++) tma_prefetch_desc(&maps.b[pl]);
     }
-    fence_proxy_async_smem();
-    if (warp == 8 && lane == 0) {
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&afull[i], 128); mbar_init(&aempty[i], 1);
-            mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
-        }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        mbar_init(bfull, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc<128>(tmem_slot);
+    if (warp == 2) tmem_alloc<128>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 && warp < 8) {
-        // ===================== A-tile producers (one output pixel per thread) =====================
-        const int r = threadIdx.x - 128;
-        const int sw = r & 7;
-        const uint32_t row_off = (r >> 3) * 1024 + sw * 128;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-            const int buf = it % NBUF;
-            const uint32_t ph = (it / NBUF) & 1;
-            mbar_wait(&aempty[buf], ph ^ 1);
-            const int n = tile >> 5;
-            const int oy = ((tile & 31) << 1) + (r >> 6), ox = r & 63;
-            const int ix0 = 2 * ox - 4;
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // weights once: 7 boxes [32 k, 64 cout] per plane
+            mbar_arrive_expect_tx(bfull, NB * C1_B_PLANE);
+            for (int pl = 0; pl < NB; pl++)
+                for (int ky = 0; ky < 7; ky++) tma_load_2d(sB + pl * C1_B_PLANE + ky * C1_B_KY, &maps.b[pl], bfull, ky * 32, 0);
+            int st = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n = tile >> 5, oy0 = (tile & 31) << 1;
+                mbar_wait(&aempty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
 #pragma unroll
-            for (int pl = 0; pl < NA; pl++) {
-                const bf16* in = (pl == 0 ? a.in_hi : a.in_lo) + (size_t)n * C1_IN * C1_IN * 4;
-                uint8_t* dst = sA + (buf * NA + pl) * C1_A_PLANE + row_off;
+                for (int pl = 0; pl < NA; pl++) {
 #pragma unroll
-                for (int ky = 0; ky < 7; ky++) {
-                    const int iy = 2 * oy + ky - 3;
-                    const bool yok = (iy >= 0) && (iy < C1_IN);
-                    uint4 v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int ix = ix0 + 2 * j;
-                        v[j] = make_uint4(0, 0, 0, 0);
-                        if (yok && ix >= 0 && ix < C1_IN) v[j] = __ldg((const uint4*)(in + ((size_t)iy * C1_IN + ix) * 4));
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int c = (ky & 1) * 4 + j;
-                        *(uint4*)(dst + (ky >> 1) * 16384 + ((c ^ sw) << 4)) = v[j];
+                    for (int ky = 0; ky < 7; ky++) {
+                        const int dy = ky - 3;           // input row = 2*oy + dy
+                        const int py = dy & 1;           // row parity -> which tensor map
+                        const int j0 = oy0 + (dy - py) / 2;
+                        tma_load_4d(sA + st * STAGE_BYTES + pl * C1_A_PLANE + ky * C1_A_KY, &maps.a[pl][py], &afull[st], 0, 0, j0, n);
                     }
                 }
+                if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&afull[buf]);
         }
-    } else if (warp == 8) {
+    } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = a.f16 ? umma_idesc_f16(128, C1_COUT) : umma_idesc_bf16(128, C1_COUT);
             const uint32_t sb0 = smem_u32(sB);
+            mbar_wait(bfull, 0);
+            int st = 0; uint32_t ph = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-                const int buf = it % NBUF;
-                const uint32_t ph = (it / NBUF) & 1;
                 const int acc = it & 1;
                 const uint32_t acc_ph = (it >> 1) & 1;
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
-                mbar_wait(&afull[buf], ph);
+                mbar_wait(&afull[st], ph);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C1_COUT;
-                const uint32_t sa0 = smem_u32(sA + buf * NA * C1_A_PLANE);
+                const uint32_t sa0 = smem_u32(sA + st * STAGE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < 14; ks++) {
-                    const uint32_t koff_a = (ks >> 2) * 16384 + (ks & 3) * 32;
-                    const uint32_t koff_b = (ks >> 2) * 8192 + (ks & 3) * 32;
-                    const uint64_t da = umma_desc_sw128(sa0 + koff_a);
-                    const uint64_t db = umma_desc_sw128(sb0 + koff_b);
+                    const uint32_t koff_a = (ks >> 1) * C1_A_KY + (ks & 1) * 32;
+                    const uint32_t koff_b = (ks >> 1) * C1_B_KY + (ks & 1) * 32;
+                    const uint64_t da = umma_desc_sw64(sa0 + koff_a);
+                    const uint64_t db = umma_desc_sw64(sb0 + koff_b);
                     umma_bf16(d_tmem, da, db, idesc, ks != 0);
-                    if (NA == 2) umma_bf16(d_tmem, umma_desc_sw128(sa0 + C1_A_PLANE + koff_a), db, idesc, 1);
-                    if (NB == 2) umma_bf16(d_tmem, da, umma_desc_sw128(sb0 + C1_B_PLANE + koff_b), idesc, 1);
+                    if (NA == 2) umma_bf16(d_tmem, umma_desc_sw64(sa0 + C1_A_PLANE + koff_a), db, idesc, 1);
+                    if (NB == 2) umma_bf16(d_tmem, da, umma_desc_sw64(sb0 + C1_B_PLANE + koff_b), idesc, 1);
                 }
-                umma_commit(&aempty[buf]);
+                umma_commit(&aempty[st]);
                 umma_commit(&tfull[acc]);
+                if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 0..3) =====================
+        // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;
         const int r = q * 32 + lane;
         int it = 0;
@@ -147,12 +135,20 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const Conv1Args a)
                 float v[16];
                 tmem_ld16(t_addr + c0, v);
                 uint32_t h[8], l[8];
+                if (a.f16) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
-                    float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
-                    if (a.f16) split2<true>(x0, x1, h[i], l[i]);
-                    else split2<false>(x0, x1, h[i], l[i]);
+                    for (int i = 0; i < 8; i++) {
+                        const float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
+                        const float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
+                        split2<true>(x0, x1, h[i], l[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
+                        const float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
+                        split2<false>(x0, x1, h[i], l[i]);
+                    }
                 }
                 uint4* op = (uint4*)(a.out_hi + o + c0);
                 op[0] = make_uint4(h[0], h[1], h[2], h[3]);
@@ -170,14 +166,14 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const Conv1Args a)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<128>(tmem_base);
+    if (warp == 2) tmem_dealloc<128>(tmem_base);
 }
 
 template <int NA, int NB>
-static int launch_c1(const Conv1Args& a, int num_sms, cudaStream_t stream) {
+static int launch_c1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream) {
     auto kern = conv1_kernel<NA, NB>;
-    constexpr int NBUF = (NA == 1) ? 2 : 1;
-    const size_t smem = 1024 + (size_t)NBUF * NA * C1_A_PLANE + (size_t)NB * C1_B_PLANE + 128;
+    constexpr int NSTAGE = (NA == 1) ? 3 : 1;
+    const size_t smem = 1024 + (size_t)NSTAGE * NA * C1_A_PLANE + (size_t)NB * C1_B_PLANE + 128;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PA_ERR_CUDA;
@@ -185,15 +181,15 @@ static int launch_c1(const Conv1Args& a, int num_sms, cudaStream_t stream) {
     }
     int grid = a.n_crops * 32;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, C1_THREADS, smem, stream>>>(a);
+    kern<<<grid, C1_THREADS, smem, stream>>>(maps, a);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
-int launch_conv1(const Conv1Args& a, int num_sms, cudaStream_t stream) {
-    const int na = a.in_lo ? 2 : 1, nb = a.w_lo ? 2 : 1;
-    if (na == 1 && nb == 1) return launch_c1<1, 1>(a, num_sms, stream);
-    if (na == 2 && nb == 1) return launch_c1<2, 1>(a, num_sms, stream);
-    if (na == 2 && nb == 2) return launch_c1<2, 2>(a, num_sms, stream);
+int launch_conv1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream) {
+    const int na = a.split_a ? 2 : 1, nb = a.split_w ? 2 : 1;
+    if (na == 1 && nb == 1) return launch_c1<1, 1>(maps, a, num_sms, stream);
+    if (na == 2 && nb == 1) return launch_c1<2, 1>(maps, a, num_sms, stream);
+    if (na == 2 && nb == 2) return launch_c1<2, 2>(maps, a, num_sms, stream);
     return PA_ERR_UNSUPPORTED;
 }
 

@@ -148,7 +148,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
                              int out_layout, int32_t* status, void* stream) {
     if (!ctx || !frames || !boxes || !out || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
     if (out_size <= 0 || out_size > 1024 || padding < 0) return PA_ERR_INVALID_ARG;
-    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4)
+    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4P)
         return PA_ERR_INVALID_ARG;
     if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
     if (n_crops == 0) return PA_OK;
@@ -163,8 +163,9 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         p.stdv[c] = std3 ? std3[c] : 1.f;
     }
     p.outp = out; p.out_dtype = out_dtype; p.out_layout = out_layout;
-    const int ch = (out_layout == PA_LAYOUT_NHWC4) ? 4 : 3;
-    p.plane_elems = (int64_t)n_crops * out_size * out_size * ch;
+    if (out_layout == PA_LAYOUT_NHWC4P && (out_dtype == PA_DTYPE_U8 || out_dtype == PA_DTYPE_F32)) return PA_ERR_UNSUPPORTED;
+    const int ch = (out_layout == PA_LAYOUT_NHWC4 || out_layout == PA_LAYOUT_NHWC4P) ? 4 : 3;
+    p.plane_elems = (int64_t)n_crops * out_size * (out_size + (out_layout == PA_LAYOUT_NHWC4P ? 8 : 0)) * ch;
     if (!status) {
         if (ctx->pp_status_cap < n_crops) {
             if (ctx->pp_status) cudaFree(ctx->pp_status);
@@ -199,7 +200,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     return PA_OK;
 }
 
-extern "C" size_t pa_crop_elems(int out_size) { return (size_t)out_size * out_size * 4; }
+extern "C" size_t pa_crop_elems(int out_size) { return (size_t)out_size * (out_size + 8) * 4; }
 
 // ------------------------------------------------------------------------------------------------ model
 struct HostTensor {
@@ -224,6 +225,7 @@ struct PlanOp {
     char name[64];
     int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool
     Conv1Args c1;
+    Conv1Maps c1maps;
     ConvMaps maps;
     ConvArgs args;
     int block_n, n_a, n_b;
@@ -577,6 +579,51 @@ static int make_map_b(pa_ctx* ctx, CUtensorMap* map, const bf16* base, int k_tot
     return PA_OK;
 }
 
+// conv1 A operand: overlapping 64-byte windows of the padded NHWC4P crop rows of one parity
+static int make_map_c1a(pa_ctx* ctx, CUtensorMap* map, const bf16* base, int n, int py) {
+    const cuuint64_t row_bytes = 136 * 4 * 2;
+    cuuint64_t dims[4] = {32, 64, 64, (cuuint64_t)n};
+    cuuint64_t strides[3] = {16, 2 * row_bytes, 128 * row_bytes};
+    cuuint32_t box[4] = {32, 64, 2, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const bf16* p = base + (size_t)py * 136 * 4;
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)p, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->last_error = "cuTensorMapEncodeTiled(conv1 A) failed: " + std::to_string((int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+static int make_map_c1b(pa_ctx* ctx, CUtensorMap* map, const bf16* w) {
+    cuuint64_t dims[2] = {256, 64};
+    cuuint64_t strides[1] = {512};
+    cuuint32_t box[2] = {32, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->last_error = "cuTensorMapEncodeTiled(conv1 B) failed: " + std::to_string((int)r); return PA_ERR_CUDA; }
+    return PA_OK;
+}
+static int plan_stem(pa_ctx* ctx, PlanOp& op, const bf16* in_hi, const bf16* in_lo, const bf16* w_hi, const bf16* w_lo,
+                     const float* scale, const float* shift, bf16* out_hi, bf16* out_lo, int n, int f16) {
+    memset(&op, 0, sizeof(op));
+    op.kind = 0;
+    snprintf(op.name, sizeof(op.name), "conv1_stem");
+    for (int py = 0; py < 2; py++) {
+        int rc = make_map_c1a(ctx, &op.c1maps.a[0][py], in_hi, n, py);
+        if (rc != PA_OK) return rc;
+        if (in_lo) { rc = make_map_c1a(ctx, &op.c1maps.a[1][py], in_lo, n, py); if (rc != PA_OK) return rc; }
+    }
+    int rc = make_map_c1b(ctx, &op.c1maps.b[0], w_hi);
+    if (rc != PA_OK) return rc;
+    if (w_lo) { rc = make_map_c1b(ctx, &op.c1maps.b[1], w_lo); if (rc != PA_OK) return rc; }
+    op.c1.scale = scale; op.c1.shift = shift;
+    op.c1.out_hi = out_hi; op.c1.out_lo = out_lo;
+    op.c1.n_crops = n; op.c1.f16 = f16;
+    op.c1.split_a = in_lo ? 1 : 0; op.c1.split_w = w_lo ? 1 : 0;
+    return PA_OK;
+}
+
 struct Act {  // an activation tensor: hi plane (+ lo plane)
     bf16* hi = nullptr;
     bf16* lo = nullptr;
@@ -660,16 +707,11 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
     m->plan.clear();
     // stem
     {
-        PlanOp op; memset(&op, 0, sizeof(op));
-        op.kind = 0;
-        snprintf(op.name, sizeof(op.name), "conv1_stem");
-        op.c1.in_hi = (const bf16*)crops;
-        op.c1.in_lo = split ? (const bf16*)crops + (size_t)n * 128 * 128 * 4 : nullptr;
-        op.c1.w_hi = m->stem_w_hi; op.c1.w_lo = m->stem_w_lo;
-        op.c1.scale = m->stem.scale; op.c1.shift = m->stem.shift;
-        op.c1.out_hi = big.hi; op.c1.out_lo = big.lo;
-        op.c1.n_crops = n;
-        op.c1.f16 = f16;
+        PlanOp op;
+        const bf16* in_hi = (const bf16*)crops;
+        const bf16* in_lo = split ? in_hi + (size_t)n * 128 * 136 * 4 : nullptr;
+        int rc = plan_stem(m->ctx, op, in_hi, in_lo, m->stem_w_hi, m->stem_w_lo, m->stem.scale, m->stem.shift, big.hi, big.lo, n, f16);
+        if (rc != PA_OK) return rc;
         m->plan.push_back(op);
     }
     {
@@ -735,7 +777,7 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
         int rc = PA_OK;
         ProfSpan sp(ctx, op.name, st);
         switch (op.kind) {
-            case 0: rc = launch_conv1(op.c1, ctx->num_sms, st); break;
+            case 0: rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, st); break;
             case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
             case 2: rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st); break;
             case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
@@ -853,25 +895,22 @@ extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n,
     std::vector<uint16_t> hi, lo;
     split_weights(packed, hi, lo, prec_f16(m.precision));
     std::vector<float> sc(scale_host, scale_host + 64), sh(shift_host, shift_host + 64);
-    Conv1Args a;
-    memset(&a, 0, sizeof(a));
-    int rc = upload(&m, hi, (uint16_t**)&a.w_hi);
-    if (rc == PA_OK && (split_w & 1)) rc = upload(&m, lo, (uint16_t**)&a.w_lo);
+    uint16_t *dw_hi = nullptr, *dw_lo = nullptr;
+    int rc = upload(&m, hi, &dw_hi);
+    if (rc == PA_OK && (split_w & 1)) rc = upload(&m, lo, &dw_lo);
     float *dsc = nullptr, *dsh = nullptr;
     if (rc == PA_OK) rc = upload(&m, sc, &dsc);
     if (rc == PA_OK) rc = upload(&m, sh, &dsh);
     if (rc == PA_OK) {
-        a.in_hi = (const bf16*)in_hi; a.in_lo = (const bf16*)in_lo;
-        a.scale = dsc; a.shift = dsh;
-        a.out_hi = (bf16*)out_hi; a.out_lo = (bf16*)out_lo;
-        a.n_crops = n;
-        a.f16 = prec_f16(m.precision) ? 1 : 0;
-        rc = launch_conv1(a, ctx->num_sms, (cudaStream_t)stream);
+        PlanOp op;
+        rc = plan_stem(ctx, op, (const bf16*)in_hi, (const bf16*)in_lo, (const bf16*)dw_hi, (const bf16*)dw_lo, dsc, dsh,
+                       (bf16*)out_hi, (bf16*)out_lo, n, prec_f16(m.precision) ? 1 : 0);
+        if (rc == PA_OK) rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, (cudaStream_t)stream);
         if (rc == PA_OK) {
             ctx->launches += 1;
             cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
             if (e != cudaSuccess) rc = cuda_fail(ctx, e, "pa_stem");
-        } else if (rc == PA_ERR_CUDA) {
+        } else if (rc == PA_ERR_CUDA && ctx->last_error.empty()) {
             cuda_fail(ctx, cudaGetLastError(), "pa_stem launch");
         }
     }

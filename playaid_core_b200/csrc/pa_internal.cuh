@@ -64,20 +64,21 @@ int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, in
 size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages);
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b);
 
-// ---------------------------------------------------------------- conv1 (7x7 stride 2, thread-built im2col)
+// ---------------------------------------------------------------- conv1 (7x7 stride 2, TMA im2col)
+struct Conv1Maps {
+    CUtensorMap a[2][2];  // [plane hi/lo][input-row parity]: [32 elems, 64 ox (16-B stride), 64 row pairs, n]
+    CUtensorMap b[2];     // [plane hi/lo] packed weights [64][256]: k = ky*32 + (kx+1)*4 + c
+};
 struct Conv1Args {
-    const bf16* in_hi;    // [n][128][128][4]
-    const bf16* in_lo;    // or nullptr
-    const bf16* w_hi;     // packed [64][256] K-major: k = ky*32 + kx8*4 + c4 (kx8 = kx+1, zero elsewhere)
-    const bf16* w_lo;     // or nullptr (3-MMA mode)
     const float* scale;   // [64]
     const float* shift;   // [64]
     bf16* out_hi;         // [n][64][64][64]
     bf16* out_lo;         // or nullptr
     int n_crops;
     int f16;              // 0 bf16, 1 IEEE half
+    int split_a, split_w; // activation / weight lo planes present
 };
-int launch_conv1(const Conv1Args& a, int num_sms, cudaStream_t stream);
+int launch_conv1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small memory-bound kernels
 int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,

@@ -236,6 +236,38 @@ __device__ __forceinline__ int align16(int v) { return (v + 15) & ~15; }
 __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut, int crop, int f, int dx, int v0, int v1, int v2) {
     // v0..v2 in source channel order; destination channel = swap ? 2-c : c
     const int out = p.out;
+    if (p.out_layout == PA_LAYOUT_NHWC4P) {
+        // 16-bit only: [crop][f][dx + 4][4] with zeroed 4-pixel borders
+        float fv[3];
+        fv[0] = lut[(p.swap_rb ? v2 : v0)]; fv[1] = lut[256 + v1]; fv[2] = lut[512 + (p.swap_rb ? v0 : v2)];
+        const bool f16 = (p.out_dtype == PA_DTYPE_F16 || p.out_dtype == PA_DTYPE_F16X2);
+        const bool split = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2);
+        uint16_t hi[3], lo[3];
+        for (int c = 0; c < 3; c++) {
+            if (f16) {
+                const __half h = __float2half_rn(fv[c]);
+                hi[c] = __half_as_ushort(h);
+                lo[c] = __half_as_ushort(__float2half_rn(__fsub_rn(fv[c], __half2float(h))));
+            } else {
+                const __nv_bfloat16 h = __float2bfloat16_rn(fv[c]);
+                hi[c] = __bfloat16_as_ushort(h);
+                lo[c] = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(fv[c], __bfloat162float(h))));
+            }
+        }
+        uint16_t* o = (uint16_t*)p.outp;
+        const int64_t rowbase = ((int64_t)crop * out + f) * (out + 8) * 4;
+        const int64_t i = rowbase + (int64_t)(dx + 4) * 4;
+        *(uint2*)(o + i) = make_uint2((uint32_t)hi[0] | ((uint32_t)hi[1] << 16), (uint32_t)hi[2]);
+        if (split) *(uint2*)(o + p.plane_elems + i) = make_uint2((uint32_t)lo[0] | ((uint32_t)lo[1] << 16), (uint32_t)lo[2]);
+        if (dx == 0 || dx == out - 1) {
+            const int64_t b = rowbase + (dx == 0 ? 0 : (int64_t)(out + 4) * 4);
+            for (int q = 0; q < 4; q++) {
+                *(uint2*)(o + b + q * 4) = make_uint2(0, 0);
+                if (split) *(uint2*)(o + p.plane_elems + b + q * 4) = make_uint2(0, 0);
+            }
+        }
+        return;
+    }
     int vv[3];
     if (p.swap_rb) { vv[0] = v2; vv[1] = v1; vv[2] = v0; } else { vv[0] = v0; vv[1] = v1; vv[2] = v2; }
     if (p.out_dtype == PA_DTYPE_U8) {
@@ -311,7 +343,8 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
 __device__ void zero_rows(const PPParams& p, int crop, int F0, int F1) {
     const int out = p.out;
     int esz = (p.out_dtype == PA_DTYPE_U8) ? 1 : (p.out_dtype == PA_DTYPE_F32 ? 4 : 2);
-    int ch = (p.out_layout == PA_LAYOUT_NHWC4) ? 4 : 3;
+    int ch = (p.out_layout == PA_LAYOUT_NHWC4 || p.out_layout == PA_LAYOUT_NHWC4P) ? 4 : 3;
+    const int wpad = (p.out_layout == PA_LAYOUT_NHWC4P) ? 8 : 0;
     int nplanes = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2) ? 2 : 1;
     for (int pl = 0; pl < nplanes; pl++) {
         uint8_t* base = (uint8_t*)p.outp + (int64_t)pl * p.plane_elems * esz;
@@ -322,8 +355,8 @@ __device__ void zero_rows(const PPParams& p, int crop, int F0, int F1) {
                 for (int64_t i = threadIdx.x; i < n; i += blockDim.x) q[i] = 0;
             }
         } else {
-            uint8_t* q = base + (((int64_t)crop * out + F0) * out) * ch * esz;
-            int64_t n = (int64_t)(F1 - F0) * out * ch * esz;
+            uint8_t* q = base + (((int64_t)crop * out + F0) * (out + wpad)) * ch * esz;
+            int64_t n = (int64_t)(F1 - F0) * (out + wpad) * ch * esz;
             for (int64_t i = threadIdx.x; i < n; i += blockDim.x) q[i] = 0;
         }
     }

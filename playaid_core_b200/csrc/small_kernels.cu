@@ -60,13 +60,56 @@ __global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
     }
 }
 
+// Single-plane fast path: post-ReLU inputs (>= 0), packed 2x16-bit maxima, 16-byte vectors.
+template <bool F16>
+__global__ void maxpool_fast_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int hin, int win, int cg) {
+    const int ho = hin / 2, wo = win / 2;
+    const int64_t total = (int64_t)n * ho * wo * cg;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        int64_t p = i / cg;
+        const int ox = (int)(p % wo); p /= wo;
+        const int oy = (int)(p % ho);
+        const int b = (int)(p / ho);
+        uint32_t m[4] = {0, 0, 0, 0};  // +0.0: valid because every window holds >= 1 non-negative value
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+            const int iy = 2 * oy + dy;
+            if (iy < 0 || iy >= hin) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                const int ix = 2 * ox + dx;
+                if (ix < 0 || ix >= win) continue;
+                const uint4 v = __ldg(in + (((int64_t)b * hin + iy) * win + ix) * cg + g);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (F16) {
+                        __half2 a = *reinterpret_cast<const __half2*>(&m[k]), c = *reinterpret_cast<const __half2*>(&w[k]);
+                        a = __hmax2(a, c);
+                        m[k] = *reinterpret_cast<uint32_t*>(&a);
+                    } else {
+                        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&m[k]), c = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+                        a = __hmax2(a, c);
+                        m[k] = *reinterpret_cast<uint32_t*>(&a);
+                    }
+                }
+            }
+        }
+        out[(((int64_t)b * ho + oy) * wo + ox) * cg + g] = make_uint4(m[0], m[1], m[2], m[3]);
+    }
+}
+
 int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
                    int f16, cudaStream_t stream) {
     const int64_t total = (int64_t)n * (hin / 2) * (win / 2) * (c / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (f16) maxpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
+    if (!in_lo) {  // the stem's ReLU output: single plane, non-negative
+        if (f16) maxpool_fast_kernel<true><<<blocks, 256, 0, stream>>>((const uint4*)in_hi, (uint4*)out_hi, n, hin, win, c / 8);
+        else maxpool_fast_kernel<false><<<blocks, 256, 0, stream>>>((const uint4*)in_hi, (uint4*)out_hi, n, hin, win, c / 8);
+    } else if (f16) maxpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
     else maxpool_kernel<false><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }

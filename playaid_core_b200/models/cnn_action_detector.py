@@ -171,14 +171,14 @@ class CNNActionDetector:
         return self._ws
 
     def features(self, crops: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """crops: 16-bit (self.act_dtype) CUDA NHWC4 [n,128,128,4] (or [2,n,128,128,4] hi/lo planes in
-        split precision), as written by `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4)`
-        -> fp32 [n,1000]."""
+        """crops: 16-bit (self.act_dtype) CUDA NHWC4P [n,128,136,4] -- 4 channels (last zero), 4 zero
+        pixels either side of every row -- or [2,n,128,136,4] hi/lo planes in split precision, as written by
+        `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4P)` -> fp32 [n,1000]."""
         if self._handle is None:
             raise _lib.PlayaidLibraryError("no weights loaded: call load_state_dict / load_from_checkpoint first")
         want = 5 if self.split else 4
-        if crops.dtype != self.act_dtype or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 128, 4):
-            raise ValueError(f"crops must be contiguous {self.act_dtype} NHWC4 [n,128,128,4] ([2,n,...] planes in split precision)")
+        if crops.dtype != self.act_dtype or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 136, 4):
+            raise ValueError(f"crops must be contiguous {self.act_dtype} NHWC4P [n,128,136,4] ([2,n,...] planes in split precision)")
         n = int(crops.shape[-4])
         if out is None:
             out = torch.empty((n, 1000), dtype=torch.float32, device=crops.device)
@@ -217,8 +217,8 @@ class CNNActionDetector:
         if S != self.sequence_length or C != 3 or H != 128 or W != 128:
             raise ValueError(f"expected [B,{self.sequence_length},3,128,128], got {tuple(x.shape)}")
         x = x.to(self._device, torch.float32).reshape(B * S, 3, H, W).permute(0, 2, 3, 1)
-        x4 = torch.zeros((B * S, H, W, 4), dtype=torch.float32, device=self._device)
-        x4[..., :3] = x
+        x4 = torch.zeros((B * S, H, W + 8, 4), dtype=torch.float32, device=self._device)
+        x4[:, :, 4 : W + 4, :3] = x
         hi = x4.to(self.act_dtype)
         if self.split:
             lo = (x4 - hi.float()).to(self.act_dtype)

@@ -35,6 +35,8 @@ def output_shape(n: int, out_size: int, dtype: int, layout: int):
         shp = (n, 3, out_size, out_size)
     elif layout == _lib.LAYOUT_NHWC4:
         shp = (n, out_size, out_size, 4)
+    elif layout == _lib.LAYOUT_NHWC4P:
+        shp = (n, out_size, out_size + 8, 4)
     else:
         shp = (n, out_size, out_size, 3)
     return (planes,) + shp if planes == 2 else shp

@@ -186,8 +186,8 @@ def test_stem_vs_torch(env, split, half):
     w = _bf(torch, torch.randn((64, 3, 7, 7), device="cuda", generator=g) / 12)
     scale = torch.rand(64, device="cuda", generator=g) + 0.5
     shift = torch.randn(64, device="cuda", generator=g) * 0.1
-    x4 = torch.zeros((N, 128, 128, 4), device="cuda")
-    x4[..., :3] = x.permute(0, 2, 3, 1)
+    x4 = torch.zeros((N, 128, 136, 4), device="cuda")   # NHWC4P: 4 zero pixels either side of a row
+    x4[:, :, 4:132, :3] = x.permute(0, 2, 3, 1)
     hi = x4.to(dt)
     lo = (x4 - hi.float()).to(dt) if split else None
     out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=dt)

@@ -121,6 +121,9 @@ def test_output_formats(torch_cuda, golden_frames):
     assert h2.dtype == torch.float16 and torch.equal(hh, want.half()) and float((hh.float() + hl.float() - want).abs().max()) < 2e-7
     h1, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F16, layout=_lib.LAYOUT_NHWC4)
     assert torch.equal(h1[..., :3].permute(0, 3, 1, 2), want.half())
+    pp, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=_lib.DTYPE_F16X2, layout=_lib.LAYOUT_NHWC4P)
+    assert tuple(pp.shape) == (2, 16, 128, 136, 4) and torch.equal(pp[:, :, :, 4:132], h2)   # conv1-ready padded layout
+    assert float(pp[:, :, :, :4].abs().max()) == 0.0 and float(pp[:, :, :, 132:].abs().max()) == 0.0
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
     ms, _ = preprocess_crops(frames, rec, 128, 30, swap_rb=True, mean=mean, std=std, dtype=_lib.DTYPE_F32, layout=_lib.LAYOUT_NCHW)
     m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
