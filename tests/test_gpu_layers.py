@@ -147,7 +147,8 @@ def test_conv_split_precision_is_fp32_accurate(env):
 
 
 def test_conv_half_format(env):
-    """IEEE-half operand planes: plain (11-bit operands) and split hi+lo (~22 bits, fp32-level)."""
+    """IEEE-half operand planes: plain (11-bit operands) and split hi+lo (~22 bits). With exact operands the
+    remaining error is the tensor core's fp32 accumulation (~4e-6 of max|ref| at K = 1152, measured)."""
     torch = env[0]
     g = torch.Generator(device="cuda").manual_seed(4)
     x = torch.randn((3, 128, 16, 16), device="cuda", generator=g)
@@ -164,13 +165,13 @@ def test_conv_half_format(env):
     assert float((yb - ref).abs().max()) / float(ref.abs().max()) < 1e-3
     ref2 = _ref(torch, x, w, 1, 1, scale, shift, res, relu=True)
     y2 = _conv(env, x, w, 1, 1, scale, shift, res, relu=True, half=True, split=True)            # hi+lo in
-    assert float((y2 - ref2).abs().max()) / float(ref2.abs().max()) < 3e-6
+    assert float((y2 - ref2).abs().max()) / float(ref2.abs().max()) < 1e-5
     y2b = _conv(env, x, w, 1, 1, scale, shift, res, relu=True, half=True, split=True, out_bf16=True)  # hi+lo out
-    assert float((y2b - ref2).abs().max()) / float(ref2.abs().max()) < 3e-6
+    assert float((y2b - ref2).abs().max()) / float(ref2.abs().max()) < 1e-5
     w32 = torch.randn((128, 128, 3, 3), device="cuda", generator=g) / 34
     ref3 = _ref(torch, x, w32, 1, 1)
     y3 = _conv(env, x, w32, 1, 1, half=True, split=True, split_w=True)                         # weights split too
-    assert float((y3 - ref3).abs().max()) / float(ref3.abs().max()) < 3e-6
+    assert float((y3 - ref3).abs().max()) / float(ref3.abs().max()) < 1e-5
 
 
 @pytest.mark.parametrize("half", [False, True])
@@ -200,5 +201,5 @@ def test_stem_vs_torch(env, split, half):
     y = (out_hi.float() + (out_lo.float() if split else 0)).permute(0, 3, 1, 2)
     ref = _ref(torch, x, w, 2, 3, scale, shift, relu=True)
     err = float((y - ref).abs().max()) / float(ref.abs().max())
-    tol = (3e-6 if half else 5e-5) if split else (1e-3 if half else 1e-2)
+    tol = (1e-5 if half else 5e-5) if split else (1e-3 if half else 1e-2)
     assert torch.isfinite(y).all() and err < tol, err
