@@ -20,7 +20,8 @@
 
 namespace pa {
 
-constexpr int C1_THREADS = 192;
+constexpr int C1_EPI_WARPS = 16;
+constexpr int C1_THREADS = (2 + C1_EPI_WARPS) * 32;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int C1_A_KY = 128 * 64;          // one filter row of the A tile: 128 rows x 64 B
 constexpr int C1_A_PLANE = 7 * C1_A_KY;    // 56 KB
 constexpr int C1_B_KY = 64 * 64;           // 64 cout rows x 64 B
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], C1_EPI_WARPS); }
         mbar_init(bfull, 1);
         fence_barrier_init();
     }
@@ -119,49 +120,53 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..17): four warps per TMEM lane quarter, 16 columns each ====
         const int q = warp & 3;
+        const int c0 = ((warp - 2) >> 2) * 16;   // this warp's fixed column chunk
         const int r = q * 32 + lane;
+        float sc[16], sh[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) { sc[i] = __ldg(a.scale + c0 + i); sh[i] = __ldg(a.shift + c0 + i); }
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
-            const int64_t o = ((int64_t)tile * 128 + r) * C1_COUT;
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C1_COUT;
-#pragma unroll 1
-            for (int c0 = 0; c0 < C1_COUT; c0 += 16) {
-                float v[16];
-                tmem_ld16(t_addr + c0, v);
-                uint32_t h[8], l[8];
-                if (a.f16) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
-                        const float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
-                        split2<true>(x0, x1, h[i], l[i]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float x0 = fmaxf(v[2 * i] * __ldg(a.scale + c0 + 2 * i) + __ldg(a.shift + c0 + 2 * i), 0.f);
-                        const float x1 = fmaxf(v[2 * i + 1] * __ldg(a.scale + c0 + 2 * i + 1) + __ldg(a.shift + c0 + 2 * i + 1), 0.f);
-                        split2<false>(x0, x1, h[i], l[i]);
-                    }
-                }
-                uint4* op = (uint4*)(a.out_hi + o + c0);
-                op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                op[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                if (a.out_lo) {
-                    uint4* lp = (uint4*)(a.out_lo + o + c0);
-                    lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
-                    lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
-                }
-            }
+            const int64_t o = ((int64_t)tile * 128 + r) * C1_COUT + c0;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C1_COUT + c0;
+            float v[16];
+            tmem_ld16(t_addr, v);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained into registers: release it early
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
+            uint32_t h[8], l[8];
+            if (a.out_lo) {
+                if (a.f16) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) split2<true>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) split2<false>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                }
+                uint4* lp = (uint4*)(a.out_lo + o);
+                lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+            } else if (a.f16) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const __half2 t = __floats2half2_rn(fminf(v[2 * i], 65504.f), fminf(v[2 * i + 1], 65504.f));
+                    h[i] = *reinterpret_cast<const uint32_t*>(&t);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            }
+            uint4* op = (uint4*)(a.out_hi + o);
+            op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            op[1] = make_uint4(h[4], h[5], h[6], h[7]);
         }
     }
     tc_fence_before();

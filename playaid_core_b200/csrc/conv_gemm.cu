@@ -10,8 +10,8 @@
 // * Both operands land in shared memory in the canonical K-major SWIZZLE_128B layout and are
 //   consumed by tcgen05.mma (M=128, N=BLOCK_N, K=16 per instruction) with the fp32 accumulator in
 //   TMEM (double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
-// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue
-//   (TMEM -> registers -> folded-BN scale/shift (+ residual) (+ ReLU) -> bf16 / fp32 global).
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..17 = epilogue
+//   (TMEM -> registers -> folded-BN scale/shift (+ residual) (+ ReLU) -> 16-bit / fp32 global).
 // * Split precision (PA_PREC_BF16X2 / X3): activations (and optionally weights) carry a bf16
 //   "lo" plane with the rounding residual; the extra products are accumulated into the same
 //   TMEM tile, reusing the staged weight tile.
@@ -23,7 +23,9 @@
 
 namespace pa {
 
-constexpr int CG_THREADS = 192;
+constexpr int CG_FIRST_EPI_WARP = 2;
+constexpr int CG_EPI_WARPS = 16;
+constexpr int CG_THREADS = (CG_FIRST_EPI_WARP + CG_EPI_WARPS) * 32;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int CG_BLOCK_M = 128;
 constexpr int CG_BLOCK_K = 64;
 constexpr int CG_A_BYTES = CG_BLOCK_M * CG_BLOCK_K * 2;  // 16 KB
@@ -40,13 +42,25 @@ int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
 }
 
 // Epilogue of one CTA: TMEM accumulator -> fp32 scale/shift (folded BN or bias) -> (+ residual) -> (ReLU)
-// -> 16-bit hi (+ lo) planes or fp32. One thread per accumulator row (= output pixel); its channels are
-// contiguous in NHWC, so every access is a 32-byte run. The residual of the next 16-column chunk is
-// prefetched while the current chunk is processed.
-template <int BLOCK_N, bool F16>
+// -> 16-bit hi (+ lo) planes or fp32. Sixteen warps: four per TMEM lane quarter, each owning every
+// fourth 16-column chunk, so TMEM / global latencies of one warp hide behind the others. One thread per
+// accumulator row (= output pixel); its channels are contiguous in NHWC, so every access is a 32-byte
+// run. The residual of a warp's next chunk is prefetched while the current one is processed.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+    if (F16) {
+        const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BLOCK_N, bool F16, bool SPLIT>
 __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
                                          int warp, int lane, int total_tiles) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int wq = (warp - CG_FIRST_EPI_WARP) >> 2;  // which of the quarter's four warps
     const int r = q * 32 + lane;
     const bool has_res = args.res_hi != nullptr;
     const bool has_res_lo = args.res_lo != nullptr;
@@ -62,7 +76,7 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
         uint4 rh0, rh1, rl0, rl1;  // residual of the current chunk
         rh0 = rh1 = rl0 = rl1 = make_uint4(0, 0, 0, 0);
         auto load_res = [&](int c0, uint4& a0, uint4& a1, uint4& b0, uint4& b1) {
-            if (has_res && row_ok && n_base + c0 + 16 <= args.cout) {
+            if (has_res && row_ok && c0 < BLOCK_N && n_base + c0 + 16 <= args.cout) {
                 const uint4* rp = (const uint4*)(args.res_hi + o_base + c0);
                 a0 = __ldg(rp); a1 = __ldg(rp + 1);
                 if (has_res_lo) {
@@ -71,28 +85,38 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
                 }
             }
         };
-        load_res(0, rh0, rh1, rl0, rl1);
+        load_res(wq * 16, rh0, rh1, rl0, rl1);
         mbar_wait(&tfull[acc], acc_ph);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        for (int c0 = wq * 16; c0 < BLOCK_N; c0 += 64) {
             float v[16];
             __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after per-row predication
             tmem_ld16(t_addr + c0, v);
             uint4 nh0, nh1, nl0, nl1;
             nh0 = nh1 = nl0 = nl1 = make_uint4(0, 0, 0, 0);
-            if (c0 + 16 < BLOCK_N) load_res(c0 + 16, nh0, nh1, nl0, nl1);
+            load_res(c0 + 64, nh0, nh1, nl0, nl1);
             const int n = n_base + c0;
             if (n < args.cout && row_ok) {
                 const bool full16 = (n + 16 <= args.cout);
                 if (args.scale) {
+                    if (full16) {
+                        const float4* sp4 = (const float4*)(args.scale + n);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) if (full16 || n + i < args.cout) v[i] *= __ldg(args.scale + n + i);
+                        for (int i = 0; i < 4; i++) { const float4 t = __ldg(sp4 + i); v[4 * i] *= t.x; v[4 * i + 1] *= t.y; v[4 * i + 2] *= t.z; v[4 * i + 3] *= t.w; }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] *= __ldg(args.scale + n + i);
+                    }
                 }
                 if (args.shift) {
+                    if (full16) {
+                        const float4* sp4 = (const float4*)(args.shift + n);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) if (full16 || n + i < args.cout) v[i] += __ldg(args.shift + n + i);
+                        for (int i = 0; i < 4; i++) { const float4 t = __ldg(sp4 + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] += __ldg(args.shift + n + i);
+                    }
                 }
                 if (has_res && full16) {
                     const uint32_t w[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
@@ -127,12 +151,17 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
                 if (args.out_hi) {
                     if (full16 && ((o & 7) == 0)) {
                         uint32_t h[8], l[8];
+                        if (SPLIT) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) split2<F16>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                            for (int i = 0; i < 8; i++) split2<F16>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
+                        }
                         uint4* op = (uint4*)(args.out_hi + o);
                         op[0] = make_uint4(h[0], h[1], h[2], h[3]);
                         op[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                        if (args.out_lo) {
+                        if (SPLIT) {
                             uint4* lp = (uint4*)(args.out_lo + o);
                             lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
                             lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
@@ -143,7 +172,7 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
                         for (int i = 0; i < 16; i++) if (n + i < args.cout) {
                             const uint16_t h0 = enc16<F16>(v[i]);
                             oh[o + i] = h0;
-                            if (ol) ol[o + i] = enc16<F16>(v[i] - dec16<F16>(h0));
+                            if (SPLIT) ol[o + i] = enc16<F16>(v[i] - dec16<F16>(h0));
                         }
                     }
                 }
@@ -184,7 +213,7 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], CG_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -262,9 +291,15 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        if (args.f16) epilogue<BLOCK_N, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
-        else epilogue<BLOCK_N, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+        // ===================== epilogue (warps 2..17) =====================
+        const bool split_out = args.out_lo != nullptr;
+        if (args.f16) {
+            if (split_out) epilogue<BLOCK_N, true, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+            else epilogue<BLOCK_N, true, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+        } else {
+            if (split_out) epilogue<BLOCK_N, false, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+            else epilogue<BLOCK_N, false, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+        }
     }
     tc_fence_before();
     __syncthreads();
