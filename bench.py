@@ -260,27 +260,37 @@ def run_gpu(args):
     h2d = BATCH_FRAMES * H * W * 3
     d2h = BATCH_FRAMES * N_FIGHTERS * 8
 
-    def e2e_step(i):
-        stage.copy_(host[i % 2], non_blocking=True)
-        st, a, b = step(stage)
+    def e2e_step(i, zero_copy):
+        if zero_copy:      # kernel reads the pinned host frames in place: only window bytes cross PCIe
+            st, a, b = step(host[i % 2])
+        else:              # stage the whole batch in HBM first
+            stage.copy_(host[i % 2], non_blocking=True)
+            st, a, b = step(stage)
         if b > a:
             n = (b - a) * N_FIGHTERS
             out_host[:n, 0].copy_(st.label[a:b].reshape(-1).float(), non_blocking=True)
             out_host[:n, 1].copy_(st.prob[a:b].reshape(-1), non_blocking=True)
 
     Ke = max(2, min(K, 10))
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(Ke):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Ke * BATCH_FRAMES / (float(t.item()) / 1e3)
+    e2e_runs = {}
+    for zero_copy in (False, True):
+        for i in range(2):
+            e2e_step(i, zero_copy)
+        barrier()
+        e0.record()
+        for i in range(Ke):
+            e2e_step(i, zero_copy)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_runs[zero_copy] = world * Ke * BATCH_FRAMES / (float(t.item()) / 1e3)
+    c_now = state["chunk"]
+    wb_e2e = float(window_bytes(px[max(c_now - Ke, 0) * BATCH_FRAMES : c_now * BATCH_FRAMES]).sum() / Ke)
+    zero_copy_wins = e2e_runs[True] >= e2e_runs[False]
+    e2e_value = max(e2e_runs.values())
+    h2d = int(wb_e2e) if zero_copy_wins else BATCH_FRAMES * H * W * 3
 
     # ---- per-kernel CUDA-event timing for the roofline (separate pass, not part of `value`)
     roofline = None
@@ -339,7 +349,10 @@ def run_gpu(args):
                        "weights": "reference architecture, seeded calibrated random init", "precision": args.precision,
                        "l2": f"inputs larger than L2: {N_RESIDENT} resident batches of 1.59 GB cycled", "parallelism": f"dp{world}"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "mode": "pinned host frames read in place by the preprocess kernel (window bytes only)" if zero_copy_wins
+                            else "whole frames staged with cudaMemcpyAsync",
+                    "staged_whole_frames": e2e_runs[False], "in_place_pinned": e2e_runs[True]},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_preprocess": roofline_pre, "kernels": kernels,
             "cpu_baseline": cpu,

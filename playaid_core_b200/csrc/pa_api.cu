@@ -21,6 +21,7 @@ struct pa_ctx {
     decltype(&cuTensorMapEncodeTiled) encode_tiled = nullptr;
     int32_t* pp_status = nullptr;  // scratch per-crop status when the caller passes none
     int pp_status_cap = 0;
+    int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { std::string name; cudaEvent_t e0, e1; };
@@ -129,12 +130,14 @@ extern "C" int pa_ctx_create(int device, pa_ctx** out) {
         return PA_ERR_CUDA;
     }
     ctx->encode_tiled = (decltype(&cuTensorMapEncodeTiled))fn;
+    if (cudaMalloc((void**)&ctx->pp_deferred, sizeof(int)) != cudaSuccess) { delete ctx; return PA_ERR_CUDA; }
     *out = ctx;
     return PA_OK;
 }
 
 extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
     if (ctx && ctx->pp_status) cudaFree(ctx->pp_status);
+    if (ctx && ctx->pp_deferred) cudaFree(ctx->pp_deferred);
     delete ctx;
     return PA_OK;
 }
@@ -179,6 +182,8 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     // pass 1: 72 KB of shared memory per CTA (3 CTAs / SM) covers the usual fighter windows;
     // pass 2: the few crops that did not fit are redone with the whole carve-out (1 CTA / SM).
     PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
+    PA_CUDA(ctx, cudaMemsetAsync(ctx->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
+    p.deferred = ctx->pp_deferred;
     p.smem_bytes = 72 * 1024;
     p.first_pass_smem = 0;
     p.defer_too_large = 1;

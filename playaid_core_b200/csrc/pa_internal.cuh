@@ -28,6 +28,7 @@ struct PPParams {
     int smem_bytes;
     int first_pass_smem;  // > 0 in the second pass: skip slabs that fit in this many bytes
     int defer_too_large;  // first pass: leave slabs that do not fit to the second pass
+    int* deferred;        // device counter of slabs the first pass left for the second
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
 

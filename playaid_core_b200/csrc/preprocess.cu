@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     const int crop = blockIdx.x / PP_SPLIT, part = blockIdx.x % PP_SPLIT;
     const int tid = threadIdx.x;
     const int out = p.out;
+    if (p.first_pass_smem > 0 && *((volatile int*)p.deferred) == 0) return;  // second pass with nothing to redo
     if (tid == 0) compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
     __syncthreads();
     const int F0 = (int)((int64_t)part * out / PP_SPLIT), F1 = (int)((int64_t)(part + 1) * out / PP_SPLIT);
@@ -483,7 +484,10 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     __syncthreads();
     if (pl.ok < 0) return;
     if (!pl.ok) {
-        if (p.defer_too_large) return;  // the second pass retries this slab with the full carve-out
+        if (p.defer_too_large) {  // the second pass retries this slab with the full carve-out
+            if (tid == 0) atomicAdd(p.deferred, 1);
+            return;
+        }
         if (tid == 0 && p.status) atomicMin(p.status + crop, PA_CROP_TOO_LARGE);
         zero_rows(p, crop, F0, F1);
         return;

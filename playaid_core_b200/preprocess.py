@@ -55,29 +55,32 @@ def preprocess_crops(
     out: torch.Tensor | None = None,
     status: torch.Tensor | None = None,
 ):
-    """Launch the fused kernel. `frames` uint8 CUDA [N,H,W,3] (rows may be pitched), `records` int32
-    CUDA [n,8]. Returns (out, status); status[i] is 1 / 0 / -2 / -7 (see playaid_b200.h)."""
-    if not (frames.is_cuda and records.is_cuda):
-        raise _lib.PlayaidLibraryError("preprocess_crops needs CUDA tensors (no CPU path)")
+    """Launch the fused kernel. `frames` uint8 [N,H,W,3] (rows may be pitched) in device memory -- or in
+    PINNED host memory, which the kernel then reads in place over PCIe (only the window bytes cross the
+    bus; no staging copy of whole 1080p frames). `records` int32 CUDA [n,8].
+    Returns (out, status); status[i] is 1 / 0 / -2 / -7 (see playaid_b200.h)."""
+    if not records.is_cuda or not (frames.is_cuda or frames.is_pinned()):
+        raise _lib.PlayaidLibraryError("preprocess_crops needs CUDA (or pinned host) frames and CUDA records (no CPU path)")
     if frames.dtype != torch.uint8 or frames.ndim != 4 or frames.shape[3] != 3 or frames.stride(3) != 1 or frames.stride(2) != 3:
         raise ValueError("frames must be uint8 [N,H,W,3] with packed pixels")
     if records.dtype != torch.int32 or records.ndim != 2 or records.shape[1] != _lib.BOX_STRIDE or not records.is_contiguous():
         raise ValueError("records must be contiguous int32 [n,8]")
-    ctx = _lib.Context.get(frames.device)
+    dev = records.device
+    ctx = _lib.Context.get(dev)
     n = int(records.shape[0])
     N, H, W, _ = frames.shape
     if out is None:
-        out = torch.empty(output_shape(n, output_size, dtype, layout), dtype=_TORCH_DTYPE[dtype], device=frames.device)
+        out = torch.empty(output_shape(n, output_size, dtype, layout), dtype=_TORCH_DTYPE[dtype], device=dev)
     if status is None:
-        status = torch.empty((n,), dtype=torch.int32, device=frames.device)
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
     mean_a = (ctypes.c_float * 3)(*[float(v) for v in mean])
     std_a = (ctypes.c_float * 3)(*[float(v) for v in std])
     fstride = frames.stride(0) if N > 1 else frames.stride(1) * H
-    with torch.cuda.device(frames.device):
+    with torch.cuda.device(dev):
         rc = ctx.lib.pa_preprocess(
             ctx.handle, frames.data_ptr(), N, H, W, frames.stride(1), fstride, records.data_ptr(), n,
             output_size, padding, 1 if swap_rb else 0, mean_a, std_a, out.data_ptr(), dtype, layout,
-            status.data_ptr(), _lib.current_stream_ptr(frames.device),
+            status.data_ptr(), _lib.current_stream_ptr(dev),
         )
     _lib.check(rc, ctx.handle, "pa_preprocess")
     return out, status

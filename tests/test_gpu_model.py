@@ -124,7 +124,7 @@ def test_clip_end_to_end_cfg1(setup):
     print(f"f16x2 max rel log-prob error {_rel(lp2, logp).max():.3e}")
     assert _rel(lp2, logp).max() < PARITY_TOL, _rel(lp2, logp).max()
     assert (r2["label"].cpu().numpy() == label).all(), "fp32-parity mode must give 100% identical labels"
-    assert np.allclose(r2["prob"].cpu().numpy(), prob, atol=2e-4)
+    assert np.allclose(r2["prob"].cpu().numpy(), prob, atol=1e-3)
 
     det1 = ActionDetector(CNNActionDetector(ACTIONS, sequence_length=7, precision="f16").eval().load_state_dict(sd))
     r1 = det1.classify_clip(frames, boxes)
