@@ -286,8 +286,7 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_runs[zero_copy] = world * Ke * BATCH_FRAMES / (float(t.item()) / 1e3)
-    c_now = state["chunk"]
-    wb_e2e = float(window_bytes(px[max(c_now - Ke, 0) * BATCH_FRAMES : c_now * BATCH_FRAMES]).sum() / Ke)
+    wb_e2e = float(window_bytes(px[: n_chunks * BATCH_FRAMES]).sum() / n_chunks)  # mean window bytes of a 256-frame step
     zero_copy_wins = e2e_runs[True] >= e2e_runs[False]
     e2e_value = max(e2e_runs.values())
     h2d = int(wb_e2e) if zero_copy_wins else BATCH_FRAMES * H * W * 3

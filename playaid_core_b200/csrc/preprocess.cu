@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             if (g.vact) fixed += nv * 8 + nv * g.v_ks * 4;
             fixed = align16(fixed) + 64;
             const int vwin = g.vact ? g.v_ks : 1;
-            const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)ceil(g.scale_y) + 2 : 2));
+            const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)floor(g.scale_y) + 2 : 2));
             auto fit = [&](int limit, int& RBo, int& CTo, int& CSo) {
                 auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
                 // ring capacities are powers of two (slot = row & (cap - 1)); very wide windows that
@@ -462,8 +462,8 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                 for (int exact = 0; exact < 2; exact++) {
                     for (int RB = exact ? 4 : 32; RB >= 1; RB >>= 1) {
                         int CT = RB + max(vwin, g.pad1 ? 0 : awin) + 1;
-                        const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 2 : RB;
-                        int CS = pr + awin + 1;
+                        const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 1 : RB;   // canvas rows one batch can complete
+                        int CS = pr + awin;
                         if (!exact) { CT = pow2(CT); CS = pow2(CS); }
                         int need = fixed + CT * tp + 64;
                         if (g.hact) need += RB * rawp + 64;
