@@ -22,6 +22,8 @@ struct pa_ctx {
     int32_t* pp_status = nullptr;  // scratch per-crop status when the caller passes none
     int pp_status_cap = 0;
     int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
+    uint8_t* pp_plan = nullptr;    // per-crop geometry + coefficient tables (preprocess_plan_kernel)
+    int pp_plan_cap = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { std::string name; cudaEvent_t e0, e1; };
@@ -138,6 +140,7 @@ extern "C" int pa_ctx_create(int device, pa_ctx** out) {
 extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
     if (ctx && ctx->pp_status) cudaFree(ctx->pp_status);
     if (ctx && ctx->pp_deferred) cudaFree(ctx->pp_deferred);
+    if (ctx && ctx->pp_plan) cudaFree(ctx->pp_plan);
     delete ctx;
     return PA_OK;
 }
@@ -184,6 +187,23 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
     PA_CUDA(ctx, cudaMemsetAsync(ctx->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
     p.deferred = ctx->pp_deferred;
+    // geometry + coefficient tables once per crop (L2-resident scratch owned by the context)
+    const int kTableStride = 24576;  // int32 per crop: windows up to ~1000 px; larger crops build tables per slab
+    const size_t geom_b = preprocess_geom_bytes();
+    if (ctx->pp_plan_cap < n_crops) {
+        if (ctx->pp_plan) cudaFree(ctx->pp_plan);
+        ctx->pp_plan = nullptr; ctx->pp_plan_cap = 0;
+        const int cap = n_crops < 1024 ? 1024 : n_crops;
+        PA_CUDA(ctx, cudaMalloc((void**)&ctx->pp_plan, (((size_t)cap * geom_b + 255) & ~(size_t)255) + (size_t)cap * kTableStride * 4));
+        ctx->pp_plan_cap = cap;
+    }
+    p.geoms = ctx->pp_plan;
+    p.tables = (int*)(ctx->pp_plan + (((size_t)ctx->pp_plan_cap * geom_b + 255) & ~(size_t)255));
+    p.table_stride = kTableStride;
+    {
+        ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
+        if (launch_preprocess_plan(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess plan launch");
+    }
     p.smem_bytes = 72 * 1024;
     p.first_pass_smem = 0;
     p.defer_too_large = 1;
@@ -201,7 +221,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         rc = launch_preprocess(p, (cudaStream_t)stream);
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch (large windows)");
-    ctx->launches += 2;
+    ctx->launches += 3;
     return PA_OK;
 }
 

@@ -29,8 +29,13 @@ struct PPParams {
     int first_pass_smem;  // > 0 in the second pass: skip slabs that fit in this many bytes
     int defer_too_large;  // first pass: leave slabs that do not fit to the second pass
     int* deferred;        // device counter of slabs the first pass left for the second
+    uint8_t* geoms;       // per-crop geometry written by preprocess_plan_kernel (or nullptr)
+    int* tables;          // per-crop coefficient tables, table_stride int32 per crop (or nullptr)
+    int table_stride;
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
+int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);
+size_t preprocess_geom_bytes();
 
 // ---------------------------------------------------------------- implicit-GEMM convolution (tcgen05 + TMA)
 // One launch = one convolution / linear layer over all crops, as D[M, Cout] = A[M, K] * W[Cout, K]^T

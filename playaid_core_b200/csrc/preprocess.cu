@@ -40,6 +40,8 @@ struct CropGeom {
     double h_scale, h_fs, h_sup;
     double v_scale, v_fs, v_sup;
     int h_ks, v_ks;
+    // per-crop coefficient tables precomputed by preprocess_plan_kernel (int32 offsets into the crop's block)
+    int tab_ok, off_h, off_v, off_x, off_y;
 };
 
 __device__ __forceinline__ double cubic(double x) {
@@ -395,6 +397,92 @@ __device__ __forceinline__ void area_rows(const CropGeom& g, int a, int& lo, int
     lo = max(lo, 0); hi = min(hi, g.sd);
 }
 
+// Table sizes shared by the plan kernel (writer) and the main kernel (reader).
+__device__ __forceinline__ int tab_ksh(const CropGeom& g) { return g.hact ? (g.h_ks <= 8 ? 8 : g.h_ks) : 0; }
+__device__ __forceinline__ int tab_xcap(const CropGeom& g) { return (g.regime == REG_GENERAL) ? (int)ceil(g.scale_x) + 2 : 0; }
+__device__ __forceinline__ int tab_ycap(const CropGeom& g) { return (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2; }
+
+// One CTA per crop: geometry + every coefficient table of the crop, once, into global memory
+// (L2-resident), so that the four slab CTAs of the main kernel only copy what they need.
+__global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) {
+    __shared__ CropGeom g;
+    const int crop = blockIdx.x, tid = threadIdx.x;
+    const int out = p.out;
+    if (tid == 0) {
+        compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
+        g.tab_ok = 0; g.off_h = g.off_v = g.off_x = g.off_y = 0;
+        if (g.status == PA_CROP_OK) {
+            int o = 0;
+            g.off_h = o; if (g.hact) o += 2 * g.nw + 4 + g.nw * tab_ksh(g);
+            o = (o + 3) & ~3;
+            g.off_v = o; if (g.vact) o += 2 * g.nh + g.nh * g.v_ks;
+            o = (o + 3) & ~3;
+            g.off_x = o;
+            if (g.regime == REG_GENERAL) o += (out + 1) + 2 * out * tab_xcap(g);
+            else if (g.regime == REG_LINEAR) o += 2 * out;
+            o = (o + 3) & ~3;
+            g.off_y = o;
+            if (g.regime == REG_GENERAL) o += g.oh + 2 * g.oh * tab_ycap(g);
+            else if (g.regime == REG_LINEAR) o += 4 * g.oh;
+            g.tab_ok = (o <= p.table_stride) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (g.status == PA_CROP_OK && g.tab_ok) {
+        int* tab = p.tables + (int64_t)crop * p.table_stride;
+        const int nw = g.nw, nh = g.nh, sd = g.sd;
+        if (g.hact) {
+            const int KSH = tab_ksh(g);
+            int* h_xmin = tab + g.off_h; int* h_n = h_xmin + nw; int* h_kk = tab + g.off_h + ((2 * nw + 3) & ~3);
+            for (int xx = tid; xx < nw; xx += 128) {
+                int xm, n;
+                bicubic_coeffs(xx, g.rw, g.h_scale, g.h_fs, g.h_sup, g.h_ks, xm, n, h_kk + (size_t)xx * KSH);
+                for (int j = g.h_ks; j < KSH; j++) h_kk[(size_t)xx * KSH + j] = 0;
+                h_xmin[xx] = xm; h_n[xx] = n;
+            }
+        }
+        if (g.vact) {
+            int* v_ymin = tab + g.off_v; int* v_n = v_ymin + nh; int* v_kk = v_n + nh;
+            for (int i = tid; i < nh; i += 128) {
+                int ym, n;
+                bicubic_coeffs(i, g.rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
+                v_ymin[i] = ym; v_n[i] = n;
+            }
+        }
+        if (g.regime == REG_GENERAL) {
+            const int xcap = tab_xcap(g), ycap = tab_ycap(g);
+            int* xt_n = tab + g.off_x; int* xt_si = xt_n + (out + 1); float* xt_al = (float*)(xt_si + out * xcap);
+            for (int dx = tid; dx < out; dx += 128) {
+                int n = area_entries(dx, sd, g.scale_x, xt_si + dx * xcap, xt_al + dx * xcap, xcap);
+                xt_n[dx] = n < xcap ? n : xcap;
+            }
+            int* yt_n = tab + g.off_y; int* yt_s = yt_n + g.oh; float* yt_b = (float*)(yt_s + g.oh * ycap);
+            for (int i = tid; i < g.oh; i += 128) {
+                int n = area_entries(i, sd, g.scale_y, yt_s + i * ycap, yt_b + i * ycap, ycap);
+                yt_n[i] = n < ycap ? n : ycap;
+            }
+        } else if (g.regime == REG_LINEAR) {
+            int* lx_s = tab + g.off_x; int* lx_a = lx_s + out;
+            for (int dx = tid; dx < out; dx += 128) {
+                int s_, a0, a1;
+                linear_coef(dx, sd, g.scale_x, g.inv_scale_x, true, s_, a0, a1);
+                lx_s[dx] = s_; lx_a[dx] = (a0 & 0xFFFF) | (a1 << 16);
+            }
+            int* yt_s = tab + g.off_y; int* yt_b = yt_s + 2 * g.oh;
+            for (int i = tid; i < g.oh; i += 128) {
+                int s_, b0, b1;
+                linear_coef(i, sd, g.scale_y, g.inv_scale_y, false, s_, b0, b1);
+                yt_s[i * 2] = s_; yt_s[i * 2 + 1] = 0;
+                yt_b[i * 2] = b0; yt_b[i * 2 + 1] = b1;
+            }
+        }
+    }
+    // publish the geometry (plain words; the main kernel launches after this one on the same stream)
+    const int* src = (const int*)&g;
+    int* dst = (int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
+    for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += 128) dst[i] = src[i];
+}
+
 __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
@@ -404,7 +492,14 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     const int tid = threadIdx.x;
     const int out = p.out;
     if (p.first_pass_smem > 0 && *((volatile int*)p.deferred) == 0) return;  // second pass with nothing to redo
-    if (tid == 0) compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
+    if (p.geoms) {
+        const int* src = (const int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
+        int* dst = (int*)&g;
+        for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += PP_THREADS) dst[i] = src[i];
+    } else if (tid == 0) {
+        compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
+        g.tab_ok = 0;
+    }
     __syncthreads();
     const int F0 = (int)((int64_t)part * out / PP_SPLIT), F1 = (int)((int64_t)(part + 1) * out / PP_SPLIT);
     if (g.status != PA_CROP_OK) {
@@ -418,9 +513,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     const int rawp = align16(rw * 3 + 15) + 32;          // 16-byte aligned copy incl. alignment shift + over-read pad
     const int tp = g.hact ? align16(nw3) + 16 : rawp;    // T row pitch (raw rows themselves when there is no H pass)
     const int sp = align16(sd3) + 16;
-    const int KSH = g.hact ? (g.h_ks <= 8 ? 8 : g.h_ks) : 0;
-    const int xcap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_x) + 2 : 0;
-    const int ycap = (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2;
+    const int KSH = tab_ksh(g), xcap = tab_xcap(g), ycap = tab_ycap(g);
 
     // ---- slab plan + shared-memory budget (thread 0)
     if (tid == 0) {
@@ -538,6 +631,42 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         float f = __fdiv_rn((float)v, 255.0f);
         lut[i] = __fdiv_rn(__fsub_rn(f, p.mean[c]), p.stdv[c]);
     }
+    if (g.tab_ok && p.tables) {
+        // copy the slices this slab needs from the crop's precomputed block (preprocess_plan_kernel)
+        const int* tab = p.tables + (int64_t)crop * p.table_stride;
+        if (g.hact) {
+            const int* gx = tab + g.off_h; const int* gk = tab + g.off_h + ((2 * nw + 3) & ~3);
+            for (int i = tid; i < nw; i += PP_THREADS) { h_xmin[i] = gx[i]; h_n[i] = gx[nw + i]; }
+            const int4* gk4 = (const int4*)gk; int4* hk4 = (int4*)h_kk;
+            if ((KSH & 3) == 0) { for (int i = tid; i < nw * KSH / 4; i += PP_THREADS) hk4[i] = __ldg(gk4 + i); }
+            else { for (int i = tid; i < nw * KSH; i += PP_THREADS) h_kk[i] = gk[i]; }
+        }
+        if (g.vact) {
+            const int* gv = tab + g.off_v;
+            for (int i = tid; i < nv; i += PP_THREADS) { v_ymin[i] = gv[P.v_begin + i]; v_n[i] = gv[nh + P.v_begin + i]; }
+            const int* gk = gv + 2 * nh + (size_t)P.v_begin * g.v_ks;
+            for (int i = tid; i < nv * g.v_ks; i += PP_THREADS) v_kk[i] = gk[i];
+        }
+        if (g.regime == REG_GENERAL) {
+            const int* gx = tab + g.off_x;
+            for (int i = tid; i < out; i += PP_THREADS) xt_n[i] = gx[i];
+            const int* gsi = gx + (out + 1); const int* gal = gsi + out * xcap;
+            for (int i = tid; i < out * xcap; i += PP_THREADS) { xt_si[i] = gsi[i]; ((int*)xt_al)[i] = gal[i]; }
+            const int* gy = tab + g.off_y;
+            for (int i = tid; i < na; i += PP_THREADS) yt_n[i] = gy[P.a0 + i];
+            const int* gys = gy + g.oh + (size_t)P.a0 * ycap; const int* gyb = gy + g.oh + (size_t)g.oh * ycap + (size_t)P.a0 * ycap;
+            for (int i = tid; i < na * ycap; i += PP_THREADS) { yt_s[i] = gys[i]; ((int*)yt_b)[i] = gyb[i]; }
+        } else if (g.regime == REG_LINEAR) {
+            const int* gx = tab + g.off_x;
+            for (int i = tid; i < out; i += PP_THREADS) {
+                lx_s[i] = gx[i];
+                const int a = gx[out + i];
+                lx_a[i * 2] = (short)(a & 0xFFFF); lx_a[i * 2 + 1] = (short)(a >> 16);
+            }
+            const int* gy = tab + g.off_y;
+            for (int i = tid; i < na * 2; i += PP_THREADS) { yt_s[i] = gy[P.a0 * 2 + i]; ((int*)yt_b)[i] = gy[2 * g.oh + P.a0 * 2 + i]; }
+        }
+    } else {
     if (g.hact) {
         for (int xx = tid; xx < nw; xx += PP_THREADS) {
             int xm, n;
@@ -574,6 +703,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             bicubic_coeffs(P.v_begin + i, rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
             v_ymin[i] = ym; v_n[i] = n;
         }
+    }
     }
     // final rows of this slab that lie in the output letterbox are black
     for (int i = tid; i < (F1 - F0) * out; i += PP_THREADS) {
@@ -885,5 +1015,11 @@ int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     preprocess_kernel<<<p.n_crops * PP_SPLIT, PP_THREADS, p.smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
+
+int launch_preprocess_plan(const PPParams& p, cudaStream_t stream) {
+    preprocess_plan_kernel<<<p.n_crops, 128, 0, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+size_t preprocess_geom_bytes() { return sizeof(CropGeom); }
 
 }  // namespace pa
