@@ -863,36 +863,51 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                     }
                 }
                 // (b) image rows
-                if (g.hact) {       // T rows are word-aligned: 4 bytes per item
+                if (g.hact) {       // T rows are 16-byte aligned: 16 bytes (4 words) per item
                     const bool aligned_dst = ((lb & 3) == 0);
-                    const int total = ns * nww;
+                    const int nq = (nw3 + 15) >> 4;                      // 16-byte items per row
+                    const uint32_t nq_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nq, 2)) + 1u;
+                    const int total = ns * nq;
                     for (int i = tid; i < total; i += PP_THREADS) {
-                        const int r = nww > 1 ? (int)__umulhi((uint32_t)i, nww_magic) : i;
-                        const int wc = i - r * nww;
+                        const int r = nq > 1 ? (int)__umulhi((uint32_t)i, nq_magic) : i;
+                        const int qc = i - r * nq;
                         const int s = s_done + r, v = s - g.oy;
                         if (v < 0 || v >= nh) continue;
-                        uint32_t o;
+                        uint32_t o[4];
                         if (g.vact) {
                             const int vi = v - P.v_begin;
                             const int32_t* k = v_kk + (size_t)vi * g.v_ks;
                             const int n = v_n[vi];
                             int slot = slotT(v_ymin[vi]);
-                            int32_t c0 = 1 << 21, c1 = 1 << 21, c2 = 1 << 21, c3 = 1 << 21;
+                            int32_t c[16];
+#pragma unroll
+                            for (int e = 0; e < 16; e++) c[e] = 1 << 21;
                             for (int j = 0; j < n; j++) {
-                                const uint32_t w = *((const uint32_t*)(T + (size_t)slot * tp) + wc);
+                                const uint4 w4 = *((const uint4*)(T + (size_t)slot * tp) + qc);
+                                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
                                 const int32_t kj = k[j];
-                                c0 += (int)__byte_perm(w, 0, 0x4440) * kj; c1 += (int)__byte_perm(w, 0, 0x4441) * kj;
-                                c2 += (int)__byte_perm(w, 0, 0x4442) * kj; c3 += (int)(w >> 24) * kj;
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    c[4 * e] += (int)__byte_perm(w[e], 0, 0x4440) * kj;
+                                    c[4 * e + 1] += (int)__byte_perm(w[e], 0, 0x4441) * kj;
+                                    c[4 * e + 2] += (int)__byte_perm(w[e], 0, 0x4442) * kj;
+                                    c[4 * e + 3] += (int)(w[e] >> 24) * kj;
+                                }
                                 if (++slot == P.CT) slot = 0;
                             }
-                            o = clip8w(c0) | (clip8w(c1) << 8) | (clip8w(c2) << 16) | (clip8w(c3) << 24);
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                o[e] = clip8w(c[4 * e]) | (clip8w(c[4 * e + 1]) << 8) | (clip8w(c[4 * e + 2]) << 16) | (clip8w(c[4 * e + 3]) << 24);
                         } else {
-                            o = *((const uint32_t*)(T + (size_t)slotT(v) * tp) + wc);
+                            const uint4 w4 = *((const uint4*)(T + (size_t)slotT(v) * tp) + qc);
+                            o[0] = w4.x; o[1] = w4.y; o[2] = w4.z; o[3] = w4.w;
                         }
                         uint8_t* drow = S + (size_t)slotS(s) * sp + lb;
-                        if (aligned_dst && wc * 4 + 4 <= nw3) *((uint32_t*)drow + wc) = o;
-                        else {
-                            for (int q = 0; q < 4; q++) if (wc * 4 + q < nw3) drow[wc * 4 + q] = (uint8_t)(o >> (8 * q));
+                        if (aligned_dst && qc * 16 + 16 <= nw3) {
+                            uint32_t* dw = (uint32_t*)drow + qc * 4;   // lb is a multiple of 4, not necessarily of 16
+                            dw[0] = o[0]; dw[1] = o[1]; dw[2] = o[2]; dw[3] = o[3];
+                        } else {
+                            for (int q = 0; q < 16; q++) if (qc * 16 + q < nw3) drow[qc * 16 + q] = (uint8_t)(o[q >> 2] >> (8 * (q & 3)));
                         }
                     }
                 } else {            // no H pass: T holds raw rows at byte offset t_off
