@@ -188,7 +188,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     PA_CUDA(ctx, cudaMemsetAsync(ctx->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
     p.deferred = ctx->pp_deferred;
     // geometry + coefficient tables once per crop (L2-resident scratch owned by the context)
-    const int kTableStride = 24576;  // int32 per crop: windows up to ~1000 px; larger crops build tables per slab
+    const int kTableStride = 40960;  // int32 per crop (160 KB): enough for a full-frame 1080p window
     const size_t geom_b = preprocess_geom_bytes();
     if (ctx->pp_plan_cap < n_crops) {
         if (ctx->pp_plan) cudaFree(ctx->pp_plan);

@@ -375,6 +375,7 @@ struct PartPlan {
     int v_begin, v_end;    // resized-image rows among those
     int t_begin, t_end;    // raw rows those need
     int RB, CT, CS;        // raw rows per batch, ring capacities (rows)
+    int h_global;          // very wide windows: leave the horizontal coefficient table in global memory
     int ok;                // 0: does not fit in shared memory
 };
 
@@ -523,6 +524,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         if (q.a1 < q.a0) q.a1 = q.a0;
         q.s_begin = q.s_end = q.v_begin = q.v_end = q.t_begin = q.t_end = 0;
         q.RB = q.CT = q.CS = 0;
+        q.h_global = 0;
         if (q.a1 > q.a0) {
             int lo, hi;
             area_rows(g, q.a0, lo, hi); q.s_begin = lo;
@@ -540,7 +542,8 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             // fixed tables
             const int na = q.a1 - q.a0, nv = q.v_end - q.v_begin;
             int fixed = 768 * 4;
-            if (g.hact) fixed += nw * 8 + nw * KSH * 4;
+            const int h_bytes = g.hact ? nw * 8 + nw * KSH * 4 : 0;
+            fixed += h_bytes;
             if (g.regime == REG_GENERAL) fixed += (out + 1) * 4 + out * xcap * 8;
             else if (g.regime == REG_LINEAR) fixed += out * 4 + align16(out * 4);
             fixed += (na + 1) * 4 + na * ycap * 8;
@@ -548,7 +551,8 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             fixed = align16(fixed) + 64;
             const int vwin = g.vact ? g.v_ks : 1;
             const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)floor(g.scale_y) + 2 : 2));
-            auto fit = [&](int limit, int& RBo, int& CTo, int& CSo) {
+            auto fit = [&](int limit_, int& RBo, int& CTo, int& CSo, bool hg = false) {
+                const int limit = limit_ + (hg ? h_bytes : 0);  // table left in global memory: its bytes are free
                 auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
                 // ring capacities are powers of two (slot = row & (cap - 1)); very wide windows that
                 // only fit with exact capacities take the modulo path
@@ -561,6 +565,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                         int need = fixed + CT * tp + 64;
                         if (g.hact) need += RB * rawp + 64;
                         if (g.pad1) need += CS * sp;
+                        if (g.regime == REG_GENERAL) need += (g.pad1 ? CS : CT) * out * 12;   // XB: x-pass rows, fp32
                         if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; return true; }
                     }
                 }
@@ -568,7 +573,10 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             };
             int rb, ct, cs;
             if (p.first_pass_smem > 0 && fit(p.first_pass_smem, rb, ct, cs)) q.ok = -1;   // done by the first pass
-            else q.ok = fit(p.smem_bytes, q.RB, q.CT, q.CS) ? 1 : 0;
+            else {
+                q.ok = fit(p.smem_bytes, q.RB, q.CT, q.CS) ? 1 : 0;
+                if (!q.ok && g.tab_ok && p.tables && g.hact && fit(p.smem_bytes, q.RB, q.CT, q.CS, true)) { q.ok = 1; q.h_global = 1; }
+            }
         } else if (p.first_pass_smem > 0) {
             q.ok = -1;
         }
@@ -593,7 +601,10 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     int off = 0;
     float* lut = (float*)(smem + off); off += 768 * 4;
     int* h_xmin = nullptr; int* h_n = nullptr; int32_t* h_kk = nullptr;
-    if (g.hact) {
+    if (g.hact && P.h_global) {
+        int* tabg = p.tables + (int64_t)crop * p.table_stride + g.off_h;
+        h_xmin = tabg; h_n = tabg + nw; h_kk = tabg + ((2 * nw + 3) & ~3);
+    } else if (g.hact) {
         h_xmin = (int*)(smem + off); off += nw * 4;
         h_n = (int*)(smem + off); off += nw * 4;
         off = align16(off);
@@ -623,6 +634,10 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     uint8_t* T = smem + off; off += P.CT * tp + 64;
     uint8_t* S = nullptr;
     if (g.pad1) { S = smem + off; off += P.CS * sp; }
+    // general area regime: horizontal area sums of every canvas row, computed once per row (fp32 [out*3])
+    float* XB = nullptr;
+    const int xbp = out * 3;
+    if (g.regime == REG_GENERAL) { off = align16(off); XB = (float*)(smem + off); off += (g.pad1 ? P.CS : P.CT) * xbp * 4; }
     if (off > p.smem_bytes) { __trap(); }  // budget computed above must hold: fail loudly
 
     // ---- tables
@@ -634,7 +649,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     if (g.tab_ok && p.tables) {
         // copy the slices this slab needs from the crop's precomputed block (preprocess_plan_kernel)
         const int* tab = p.tables + (int64_t)crop * p.table_stride;
-        if (g.hact) {
+        if (g.hact && !P.h_global) {
             const int* gx = tab + g.off_h; const int* gk = tab + g.off_h + ((2 * nw + 3) & ~3);
             for (int i = tid; i < nw; i += PP_THREADS) { h_xmin[i] = gx[i]; h_n[i] = gx[nw + i]; }
             const int4* gk4 = (const int4*)gk; int4* hk4 = (int4*)h_kk;
@@ -740,6 +755,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     int t_done = P.t_begin;     // raw rows [t_begin, t_done) have been through the H pass (ring T)
     int s_done = P.s_begin;     // canvas rows [s_begin, s_done) produced (ring S)
     int a_done = P.a0;          // area rows emitted
+    int xb_done = g.pad1 ? P.s_begin : P.t_begin;  // canvas rows whose x-pass is in XB (general regime)
 
     auto t_needed_from = [&](int s_next) -> int {   // lowest raw row still needed once canvas rows < s_next exist
         int v = min(max(s_next - g.oy, P.v_begin), P.v_end);
@@ -940,6 +956,32 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         }
         const int cv_done = g.pad1 ? s_done : t_done;
 
+        // ================= 2b. general area regime: x-pass of the canvas rows that just became available
+        if (g.regime == REG_GENERAL) {
+            const int nrow = cv_done - xb_done;
+            for (int i = tid; i < nrow * out; i += PP_THREADS) {
+                const int r = out > 1 ? (int)__umulhi((uint32_t)i, out_magic) : i;
+                const int dx = i - r * out;
+                const int cr = xb_done + r;
+                const uint8_t* row = CV + (size_t)slotCV(cr) * CVp;
+                const int nx = xt_n[dx];
+                const int* xsi = xt_si + dx * xcap;
+                const float* xal = xt_al + dx * xcap;
+                float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                for (int k = 0; k < nx; k++) {
+                    const uint8_t* q = row + xsi[k] * 3;
+                    const float al = xal[k];
+                    b0 = __fadd_rn(b0, __fmul_rn((float)q[0], al));
+                    b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
+                    b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
+                }
+                float* o = XB + (size_t)slotCV(cr) * xbp + dx * 3;
+                o[0] = b0; o[1] = b1; o[2] = b2;
+            }
+            xb_done = cv_done;
+            __syncthreads();
+        }
+
         // ================= 3. area pass for every output row whose canvas rows are ready
         int a_new = a_done;
         while (a_new < P.a1) {
@@ -971,22 +1013,12 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                     v0 = sat_u8f(__fmul_rn((float)a0, sc)); v1 = sat_u8f(__fmul_rn((float)a1, sc)); v2 = sat_u8f(__fmul_rn((float)a2, sc));
                 }
             } else if (g.regime == REG_GENERAL) {
-                const int nx = xt_n[dx];
-                const int* xsi = xt_si + dx * xcap;
-                const float* xal = xt_al + dx * xcap;
                 const int ny = yt_n[ai];
                 float m0 = 0.f, m1 = 0.f, m2 = 0.f;
                 for (int j = 0; j < ny; j++) {
                     const float beta = yt_b[ai * ycap + j];
-                    const uint8_t* row = CV + (size_t)slotCV(yt_s[ai * ycap + j]) * CVp;
-                    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-                    for (int k = 0; k < nx; k++) {
-                        const uint8_t* q = row + xsi[k] * 3;
-                        const float al = xal[k];
-                        b0 = __fadd_rn(b0, __fmul_rn((float)q[0], al));
-                        b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
-                        b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
-                    }
+                    const float* xr = XB + (size_t)slotCV(yt_s[ai * ycap + j]) * xbp + dx * 3;
+                    const float b0 = xr[0], b1 = xr[1], b2 = xr[2];
                     if (j == 0) { m0 = __fmul_rn(beta, b0); m1 = __fmul_rn(beta, b1); m2 = __fmul_rn(beta, b2); }
                     else {
                         m0 = __fadd_rn(m0, __fmul_rn(beta, b0)); m1 = __fadd_rn(m1, __fmul_rn(beta, b1)); m2 = __fadd_rn(m2, __fmul_rn(beta, b2));
