@@ -182,7 +182,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         status = ctx->pp_status;
     }
     p.status = status;
-    // pass 1: 72 KB of shared memory per CTA (3 CTAs / SM) covers the usual fighter windows;
+    // pass 1: 108 KB of shared memory per 384-thread CTA (2 CTAs / SM) covers the usual fighter windows;
     // pass 2: the few crops that did not fit are redone with the whole carve-out (1 CTA / SM).
     PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
     PA_CUDA(ctx, cudaMemsetAsync(ctx->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
@@ -204,7 +204,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
         if (launch_preprocess_plan(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess plan launch");
     }
-    p.smem_bytes = 72 * 1024;
+    p.smem_bytes = 108 * 1024;
     p.first_pass_smem = 0;
     p.defer_too_large = 1;
     int rc;
@@ -214,7 +214,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
     p.smem_bytes = 224 * 1024;
-    p.first_pass_smem = 72 * 1024;
+    p.first_pass_smem = 108 * 1024;
     p.defer_too_large = 0;
     {
         ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);

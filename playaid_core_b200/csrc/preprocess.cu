@@ -22,7 +22,7 @@
 
 namespace pa {
 
-constexpr int PP_THREADS = 256;
+constexpr int PP_THREADS = 384;
 constexpr int PP_SPLIT = 4;
 
 enum { REG_COPY = 0, REG_FAST = 1, REG_GENERAL = 2, REG_LINEAR = 3 };
@@ -375,6 +375,7 @@ struct PartPlan {
     int v_begin, v_end;    // resized-image rows among those
     int t_begin, t_end;    // raw rows those need
     int RB, CT, CS;        // raw rows per batch, ring capacities (rows)
+    int CX;                // capacity of the fp32 x-pass ring (general area regime), else 0
     int h_global;          // very wide windows: leave the horizontal coefficient table in global memory
     int ok;                // 0: does not fit in shared memory
 };
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += 128) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParams p) {
+__global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
     __shared__ PartPlan pl;
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         q.a0 = max(F0 - g.oy2, 0); q.a1 = min(F1 - g.oy2, g.oh);
         if (q.a1 < q.a0) q.a1 = q.a0;
         q.s_begin = q.s_end = q.v_begin = q.v_end = q.t_begin = q.t_end = 0;
-        q.RB = q.CT = q.CS = 0;
+        q.RB = q.CT = q.CS = q.CX = 0;
         q.h_global = 0;
         if (q.a1 > q.a0) {
             int lo, hi;
@@ -546,36 +547,41 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
             fixed += h_bytes;
             if (g.regime == REG_GENERAL) fixed += (out + 1) * 4 + out * xcap * 8;
             else if (g.regime == REG_LINEAR) fixed += out * 4 + align16(out * 4);
-            fixed += (na + 1) * 4 + na * ycap * 8;
+            fixed += (na + 1) * 4 + na * ycap * 8 + na * 8;
             if (g.vact) fixed += nv * 8 + nv * g.v_ks * 4;
             fixed = align16(fixed) + 64;
             const int vwin = g.vact ? g.v_ks : 1;
             const int awin = (g.regime == REG_COPY) ? 1 : (g.regime == REG_FAST ? g.isy : (g.regime == REG_GENERAL ? (int)floor(g.scale_y) + 2 : 2));
-            auto fit = [&](int limit_, int& RBo, int& CTo, int& CSo, bool hg = false) {
+            auto fit = [&](int limit_, int& RBo, int& CTo, int& CSo, int& CXo, bool hg = false) {
                 const int limit = limit_ + (hg ? h_bytes : 0);  // table left in global memory: its bytes are free
                 auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
+                const bool gen = (g.regime == REG_GENERAL);
                 // ring capacities are powers of two (slot = row & (cap - 1)); very wide windows that
                 // only fit with exact capacities take the modulo path
                 for (int exact = 0; exact < 2; exact++) {
                     for (int RB = exact ? 4 : 32; RB >= 1; RB >>= 1) {
                         int CT = RB + max(vwin, g.pad1 ? 0 : awin) + 1;
                         const int pr = g.vact ? (int)ceil(RB / g.v_scale) + 1 : RB;   // canvas rows one batch can complete
-                        int CS = pr + awin;
-                        if (!exact) { CT = pow2(CT); CS = pow2(CS); }
+                        // general regime: S only holds the rows of the current batch (their x-pass goes to the
+                        // fp32 ring XB, which is what the y-pass keeps); other regimes read S directly
+                        int CS = gen ? pr : pr + awin;
+                        int CX = gen ? (g.pad1 ? pr + awin : CT) : 0;
+                        if (!exact) { CT = pow2(CT); CS = pow2(CS); if (gen) CX = g.pad1 ? pow2(CX) : CT; }
+                        else if (gen && !g.pad1) CX = CT;
                         int need = fixed + CT * tp + 64;
                         if (g.hact) need += RB * rawp + 64;
                         if (g.pad1) need += CS * sp;
-                        if (g.regime == REG_GENERAL) need += (g.pad1 ? CS : CT) * out * 12;   // XB: x-pass rows, fp32
-                        if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; return true; }
+                        need += CX * out * 12 + 16;
+                        if (need <= limit) { RBo = RB; CTo = CT; CSo = CS; CXo = CX; return true; }
                     }
                 }
                 return false;
             };
-            int rb, ct, cs;
-            if (p.first_pass_smem > 0 && fit(p.first_pass_smem, rb, ct, cs)) q.ok = -1;   // done by the first pass
+            int rb, ct, cs, cx;
+            if (p.first_pass_smem > 0 && fit(p.first_pass_smem, rb, ct, cs, cx)) q.ok = -1;   // done by the first pass
             else {
-                q.ok = fit(p.smem_bytes, q.RB, q.CT, q.CS) ? 1 : 0;
-                if (!q.ok && g.tab_ok && p.tables && g.hact && fit(p.smem_bytes, q.RB, q.CT, q.CS, true)) { q.ok = 1; q.h_global = 1; }
+                q.ok = fit(p.smem_bytes, q.RB, q.CT, q.CS, q.CX) ? 1 : 0;
+                if (!q.ok && g.tab_ok && p.tables && g.hact && fit(p.smem_bytes, q.RB, q.CT, q.CS, q.CX, true)) { q.ok = 1; q.h_global = 1; }
             }
         } else if (p.first_pass_smem > 0) {
             q.ok = -1;
@@ -619,6 +625,8 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         lx_s = (int*)(smem + off); off += out * 4;
         lx_a = (short*)(smem + off); off += align16(out * 4);
     }
+    int* ar_lo = (int*)(smem + off); off += na * 4;   // canvas-row span [lo, hi) of every area row of the slab
+    int* ar_hi = (int*)(smem + off); off += na * 4;
     int* yt_n = (int*)(smem + off); off += (na + 1) * 4;
     int* yt_s = (int*)(smem + off); off += na * ycap * 4;
     float* yt_b = (float*)(smem + off); off += na * ycap * 4;
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     // general area regime: horizontal area sums of every canvas row, computed once per row (fp32 [out*3])
     float* XB = nullptr;
     const int xbp = out * 3;
-    if (g.regime == REG_GENERAL) { off = align16(off); XB = (float*)(smem + off); off += (g.pad1 ? P.CS : P.CT) * xbp * 4; }
+    if (g.regime == REG_GENERAL) { off = align16(off); XB = (float*)(smem + off); off += P.CX * xbp * 4; }
     if (off > p.smem_bytes) { __trap(); }  // budget computed above must hold: fail loudly
 
     // ---- tables
@@ -720,6 +728,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
         }
     }
     }
+    for (int i = tid; i < na; i += PP_THREADS) { int lo, hi; area_rows(g, P.a0 + i, lo, hi); ar_lo[i] = lo; ar_hi[i] = hi; }
     // final rows of this slab that lie in the output letterbox are black
     for (int i = tid; i < (F1 - F0) * out; i += PP_THREADS) {
         const int f = F0 + i / out, dx = i % out;
@@ -751,6 +760,8 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     auto slotT = [&](int row) { return ct_p2 ? (row & (P.CT - 1)) : (row % P.CT); };
     auto slotS = [&](int row) { return cs_p2 ? (row & (P.CS - 1)) : (row % P.CS); };
     auto slotCV = [&](int row) { return g.pad1 ? slotS(row) : slotT(row); };
+    const bool cx_p2 = P.CX > 0 && (P.CX & (P.CX - 1)) == 0;
+    auto slotX = [&](int row) { return cx_p2 ? (row & (P.CX - 1)) : (row % max(P.CX, 1)); };
 
     int t_done = P.t_begin;     // raw rows [t_begin, t_done) have been through the H pass (ring T)
     int s_done = P.s_begin;     // canvas rows [s_begin, s_done) produced (ring S)
@@ -766,7 +777,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
     while (a_done < P.a1) {
         // ================= 1. load a batch of raw rows, horizontal pass -> T ring
         {
-            const int t_keep = g.pad1 ? t_needed_from(s_done) : ([&] { int lo, hi; area_rows(g, a_done, lo, hi); return lo; })();
+            const int t_keep = g.pad1 ? t_needed_from(s_done) : ar_lo[a_done - P.a0];
             int nb = min(P.RB, P.t_end - t_done);
             nb = min(nb, P.CT - (t_done - t_keep));
             if (nb > 0) {
@@ -852,10 +863,10 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
 
         // ================= 2. vertical pass: canvas rows whose taps are all in T -> S ring
         if (g.pad1) {
-            int lo_keep, hi_tmp;
-            area_rows(g, a_done, lo_keep, hi_tmp);          // lowest canvas row still needed
+            const int lo_keep = ar_lo[a_done - P.a0];       // lowest canvas row still needed
+            const int keep_cap = (g.regime == REG_GENERAL) ? P.CX : P.CS;
             int s_new = s_done;
-            while (s_new < P.s_end && (s_new - lo_keep) < P.CS) {
+            while (s_new < P.s_end && (s_new - lo_keep) < keep_cap && (s_new - s_done) < P.CS) {
                 const int v = s_new - g.oy;
                 if (v >= 0 && v < nh) {
                     const int need = g.vact ? (v_ymin[v - P.v_begin] + v_n[v - P.v_begin]) : (v + 1);
@@ -975,7 +986,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                     b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
                     b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
                 }
-                float* o = XB + (size_t)slotCV(cr) * xbp + dx * 3;
+                float* o = XB + (size_t)slotX(cr) * xbp + dx * 3;
                 o[0] = b0; o[1] = b1; o[2] = b2;
             }
             xb_done = cv_done;
@@ -984,12 +995,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
 
         // ================= 3. area pass for every output row whose canvas rows are ready
         int a_new = a_done;
-        while (a_new < P.a1) {
-            int lo, hi;
-            area_rows(g, a_new, lo, hi);
-            if (hi > cv_done) break;
-            a_new++;
-        }
+        while (a_new < P.a1 && ar_hi[a_new - P.a0] <= cv_done) a_new++;
         const int npix = (a_new - a_done) * out;
         for (int i = tid; i < npix; i += PP_THREADS) {
             const int ar = out > 1 ? (int)__umulhi((uint32_t)i, out_magic) : i;
@@ -1017,7 +1023,7 @@ __global__ void __launch_bounds__(PP_THREADS, 3) preprocess_kernel(const PPParam
                 float m0 = 0.f, m1 = 0.f, m2 = 0.f;
                 for (int j = 0; j < ny; j++) {
                     const float beta = yt_b[ai * ycap + j];
-                    const float* xr = XB + (size_t)slotCV(yt_s[ai * ycap + j]) * xbp + dx * 3;
+                    const float* xr = XB + (size_t)slotX(yt_s[ai * ycap + j]) * xbp + dx * 3;
                     const float b0 = xr[0], b1 = xr[1], b2 = xr[2];
                     if (j == 0) { m0 = __fmul_rn(beta, b0); m1 = __fmul_rn(beta, b1); m2 = __fmul_rn(beta, b2); }
                     else {
