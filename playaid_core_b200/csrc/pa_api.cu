@@ -3,6 +3,7 @@
 // workspace carving and kernel sequencing. No PyTorch types cross this boundary.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -204,7 +205,19 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
         if (launch_preprocess_plan(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess plan launch");
     }
-    p.smem_bytes = 108 * 1024;
+    // tunables (defaults measured on B200; PA_PP_* environment variables override for experiments)
+    static int cfg_threads = 0, cfg_smem_kb = 0, cfg_xb = 0;
+    if (!cfg_threads) {
+        const char* e;
+        cfg_threads = (e = getenv("PA_PP_THREADS")) ? atoi(e) : 256;
+        cfg_smem_kb = (e = getenv("PA_PP_SMEM_KB")) ? atoi(e) : 72;
+        cfg_xb = (e = getenv("PA_PP_XB")) ? atoi(e) : 0;
+        if (cfg_threads != 256 && cfg_threads != 384) cfg_threads = 256;
+        if (cfg_smem_kb < 48 || cfg_smem_kb > 224) cfg_smem_kb = 72;
+    }
+    p.threads = cfg_threads;
+    p.use_xb = cfg_xb;
+    p.smem_bytes = cfg_smem_kb * 1024;
     p.first_pass_smem = 0;
     p.defer_too_large = 1;
     int rc;
@@ -214,7 +227,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
     p.smem_bytes = 224 * 1024;
-    p.first_pass_smem = 108 * 1024;
+    p.first_pass_smem = cfg_smem_kb * 1024;
     p.defer_too_large = 0;
     {
         ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);

@@ -32,6 +32,8 @@ struct PPParams {
     uint8_t* geoms;       // per-crop geometry written by preprocess_plan_kernel (or nullptr)
     int* tables;          // per-crop coefficient tables, table_stride int32 per crop (or nullptr)
     int table_stride;
+    int threads;          // CTA size of the main kernel: 256 (3 CTAs/SM) or 384 (2 CTAs/SM)
+    int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
 int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);

@@ -22,7 +22,7 @@
 
 namespace pa {
 
-constexpr int PP_THREADS = 384;
+constexpr int PP_MAX_THREADS = 384;
 constexpr int PP_SPLIT = 4;
 
 enum { REG_COPY = 0, REG_FAST = 1, REG_GENERAL = 2, REG_LINEAR = 3 };
@@ -485,19 +485,20 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += 128) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParams p) {
+__global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
     __shared__ PartPlan pl;
 
     const int crop = blockIdx.x / PP_SPLIT, part = blockIdx.x % PP_SPLIT;
     const int tid = threadIdx.x;
+    const int NT = blockDim.x;   // 256 or 384 threads (runtime: see pa_preprocess)
     const int out = p.out;
     if (p.first_pass_smem > 0 && *((volatile int*)p.deferred) == 0) return;  // second pass with nothing to redo
     if (p.geoms) {
         const int* src = (const int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
         int* dst = (int*)&g;
-        for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += PP_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += NT) dst[i] = src[i];
     } else if (tid == 0) {
         compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
         g.tab_ok = 0;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
             auto fit = [&](int limit_, int& RBo, int& CTo, int& CSo, int& CXo, bool hg = false) {
                 const int limit = limit_ + (hg ? h_bytes : 0);  // table left in global memory: its bytes are free
                 auto pow2 = [](int v) { int q = 1; while (q < v) q <<= 1; return q; };
-                const bool gen = (g.regime == REG_GENERAL);
+                const bool gen = (g.regime == REG_GENERAL) && p.use_xb;
                 // ring capacities are powers of two (slot = row & (cap - 1)); very wide windows that
                 // only fit with exact capacities take the modulo path
                 for (int exact = 0; exact < 2; exact++) {
@@ -645,11 +646,11 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
     // general area regime: horizontal area sums of every canvas row, computed once per row (fp32 [out*3])
     float* XB = nullptr;
     const int xbp = out * 3;
-    if (g.regime == REG_GENERAL) { off = align16(off); XB = (float*)(smem + off); off += P.CX * xbp * 4; }
+    if (P.CX > 0) { off = align16(off); XB = (float*)(smem + off); off += P.CX * xbp * 4; }
     if (off > p.smem_bytes) { __trap(); }  // budget computed above must hold: fail loudly
 
     // ---- tables
-    for (int i = tid; i < 768; i += PP_THREADS) {
+    for (int i = tid; i < 768; i += NT) {
         int c = i >> 8, v = i & 255;
         float f = __fdiv_rn((float)v, 255.0f);
         lut[i] = __fdiv_rn(__fsub_rn(f, p.mean[c]), p.stdv[c]);
@@ -659,39 +660,39 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         const int* tab = p.tables + (int64_t)crop * p.table_stride;
         if (g.hact && !P.h_global) {
             const int* gx = tab + g.off_h; const int* gk = tab + g.off_h + ((2 * nw + 3) & ~3);
-            for (int i = tid; i < nw; i += PP_THREADS) { h_xmin[i] = gx[i]; h_n[i] = gx[nw + i]; }
+            for (int i = tid; i < nw; i += NT) { h_xmin[i] = gx[i]; h_n[i] = gx[nw + i]; }
             const int4* gk4 = (const int4*)gk; int4* hk4 = (int4*)h_kk;
-            if ((KSH & 3) == 0) { for (int i = tid; i < nw * KSH / 4; i += PP_THREADS) hk4[i] = __ldg(gk4 + i); }
-            else { for (int i = tid; i < nw * KSH; i += PP_THREADS) h_kk[i] = gk[i]; }
+            if ((KSH & 3) == 0) { for (int i = tid; i < nw * KSH / 4; i += NT) hk4[i] = __ldg(gk4 + i); }
+            else { for (int i = tid; i < nw * KSH; i += NT) h_kk[i] = gk[i]; }
         }
         if (g.vact) {
             const int* gv = tab + g.off_v;
-            for (int i = tid; i < nv; i += PP_THREADS) { v_ymin[i] = gv[P.v_begin + i]; v_n[i] = gv[nh + P.v_begin + i]; }
+            for (int i = tid; i < nv; i += NT) { v_ymin[i] = gv[P.v_begin + i]; v_n[i] = gv[nh + P.v_begin + i]; }
             const int* gk = gv + 2 * nh + (size_t)P.v_begin * g.v_ks;
-            for (int i = tid; i < nv * g.v_ks; i += PP_THREADS) v_kk[i] = gk[i];
+            for (int i = tid; i < nv * g.v_ks; i += NT) v_kk[i] = gk[i];
         }
         if (g.regime == REG_GENERAL) {
             const int* gx = tab + g.off_x;
-            for (int i = tid; i < out; i += PP_THREADS) xt_n[i] = gx[i];
+            for (int i = tid; i < out; i += NT) xt_n[i] = gx[i];
             const int* gsi = gx + (out + 1); const int* gal = gsi + out * xcap;
-            for (int i = tid; i < out * xcap; i += PP_THREADS) { xt_si[i] = gsi[i]; ((int*)xt_al)[i] = gal[i]; }
+            for (int i = tid; i < out * xcap; i += NT) { xt_si[i] = gsi[i]; ((int*)xt_al)[i] = gal[i]; }
             const int* gy = tab + g.off_y;
-            for (int i = tid; i < na; i += PP_THREADS) yt_n[i] = gy[P.a0 + i];
+            for (int i = tid; i < na; i += NT) yt_n[i] = gy[P.a0 + i];
             const int* gys = gy + g.oh + (size_t)P.a0 * ycap; const int* gyb = gy + g.oh + (size_t)g.oh * ycap + (size_t)P.a0 * ycap;
-            for (int i = tid; i < na * ycap; i += PP_THREADS) { yt_s[i] = gys[i]; ((int*)yt_b)[i] = gyb[i]; }
+            for (int i = tid; i < na * ycap; i += NT) { yt_s[i] = gys[i]; ((int*)yt_b)[i] = gyb[i]; }
         } else if (g.regime == REG_LINEAR) {
             const int* gx = tab + g.off_x;
-            for (int i = tid; i < out; i += PP_THREADS) {
+            for (int i = tid; i < out; i += NT) {
                 lx_s[i] = gx[i];
                 const int a = gx[out + i];
                 lx_a[i * 2] = (short)(a & 0xFFFF); lx_a[i * 2 + 1] = (short)(a >> 16);
             }
             const int* gy = tab + g.off_y;
-            for (int i = tid; i < na * 2; i += PP_THREADS) { yt_s[i] = gy[P.a0 * 2 + i]; ((int*)yt_b)[i] = gy[2 * g.oh + P.a0 * 2 + i]; }
+            for (int i = tid; i < na * 2; i += NT) { yt_s[i] = gy[P.a0 * 2 + i]; ((int*)yt_b)[i] = gy[2 * g.oh + P.a0 * 2 + i]; }
         }
     } else {
     if (g.hact) {
-        for (int xx = tid; xx < nw; xx += PP_THREADS) {
+        for (int xx = tid; xx < nw; xx += NT) {
             int xm, n;
             bicubic_coeffs(xx, rw, g.h_scale, g.h_fs, g.h_sup, g.h_ks, xm, n, h_kk + (size_t)xx * KSH);
             for (int j = g.h_ks; j < KSH; j++) h_kk[(size_t)xx * KSH + j] = 0;
@@ -699,21 +700,21 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         }
     }
     if (g.regime == REG_GENERAL) {
-        for (int dx = tid; dx < out; dx += PP_THREADS) {
+        for (int dx = tid; dx < out; dx += NT) {
             int n = area_entries(dx, sd, g.scale_x, xt_si + dx * xcap, xt_al + dx * xcap, xcap);
             xt_n[dx] = n < xcap ? n : xcap;
         }
-        for (int i = tid; i < na; i += PP_THREADS) {
+        for (int i = tid; i < na; i += NT) {
             int n = area_entries(P.a0 + i, sd, g.scale_y, yt_s + i * ycap, yt_b + i * ycap, ycap);
             yt_n[i] = n < ycap ? n : ycap;
         }
     } else if (g.regime == REG_LINEAR) {
-        for (int dx = tid; dx < out; dx += PP_THREADS) {
+        for (int dx = tid; dx < out; dx += NT) {
             int s, a0, a1;
             linear_coef(dx, sd, g.scale_x, g.inv_scale_x, true, s, a0, a1);
             lx_s[dx] = s; lx_a[dx * 2] = (short)a0; lx_a[dx * 2 + 1] = (short)a1;
         }
-        for (int i = tid; i < na; i += PP_THREADS) {
+        for (int i = tid; i < na; i += NT) {
             int s, b0, b1;
             linear_coef(P.a0 + i, sd, g.scale_y, g.inv_scale_y, false, s, b0, b1);
             yt_s[i * 2] = s;
@@ -721,16 +722,16 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         }
     }
     if (g.vact) {
-        for (int i = tid; i < nv; i += PP_THREADS) {
+        for (int i = tid; i < nv; i += NT) {
             int ym, n;
             bicubic_coeffs(P.v_begin + i, rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
             v_ymin[i] = ym; v_n[i] = n;
         }
     }
     }
-    for (int i = tid; i < na; i += PP_THREADS) { int lo, hi; area_rows(g, P.a0 + i, lo, hi); ar_lo[i] = lo; ar_hi[i] = hi; }
+    for (int i = tid; i < na; i += NT) { int lo, hi; area_rows(g, P.a0 + i, lo, hi); ar_lo[i] = lo; ar_hi[i] = hi; }
     // final rows of this slab that lie in the output letterbox are black
-    for (int i = tid; i < (F1 - F0) * out; i += PP_THREADS) {
+    for (int i = tid; i < (F1 - F0) * out; i += NT) {
         const int f = F0 + i / out, dx = i % out;
         const int dy = f - g.oy2;
         if (dy < 0 || dy >= g.oh) store_pixel(p, lut, crop, f, dx, 0, 0, 0);
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                 if (rw > 0) {
                     if (vec_ok) {
                         const int total = nb * chunks;
-                        for (int i = tid; i < total; i += PP_THREADS) {
+                        for (int i = tid; i < total; i += NT) {
                             const int r = chunks > 1 ? (int)__umulhi((uint32_t)i, ch_magic) : i;
                             const int c = i - r * chunks;
                             const int t = t_done + r;
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                         }
                     } else {
                         const int total = nb * rw * 3;
-                        for (int i = tid; i < total; i += PP_THREADS) {
+                        for (int i = tid; i < total; i += NT) {
                             const int r = i / (rw * 3), c = i - r * (rw * 3);
                             const int t = t_done + r;
                             dstbase[(size_t)(g.hact ? r : slotT(t)) * dpitch + c] = fbase[row0 + (int64_t)t * p.pitch + c];
@@ -814,7 +815,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                     __syncthreads();
                     const int total = nb * nw;
                     if (h_fast) {
-                        for (int i = tid; i < total; i += PP_THREADS) {
+                        for (int i = tid; i < total; i += NT) {
                             const int r = nw > 1 ? (int)__umulhi((uint32_t)i, nw_magic) : i;
                             const int xx = i - r * nw;
                             const int4 ka = *(const int4*)(h_kk + (size_t)xx * 8);
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                             d[0] = (uint8_t)clip8w(s0); d[1] = (uint8_t)clip8w(s1); d[2] = (uint8_t)clip8w(s2);
                         }
                     } else {
-                        for (int i = tid; i < total; i += PP_THREADS) {
+                        for (int i = tid; i < total; i += NT) {
                             const int r = i / nw, xx = i - r * nw;
                             const uint8_t* src = RAW + (size_t)r * rawp + shift + h_xmin[xx] * 3;
                             const int32_t* k = h_kk + (size_t)xx * KSH;
@@ -864,7 +865,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         // ================= 2. vertical pass: canvas rows whose taps are all in T -> S ring
         if (g.pad1) {
             const int lo_keep = ar_lo[a_done - P.a0];       // lowest canvas row still needed
-            const int keep_cap = (g.regime == REG_GENERAL) ? P.CX : P.CS;
+            const int keep_cap = (P.CX > 0) ? P.CX : P.CS;
             int s_new = s_done;
             while (s_new < P.s_end && (s_new - lo_keep) < keep_cap && (s_new - s_done) < P.CS) {
                 const int v = s_new - g.oy;
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
             if (ns > 0) {
                 // (a) black rows and letterbox borders
                 const int lb = g.ox * 3, rb = g.ox * 3 + nw3;   // data occupies [lb, rb) of an image row
-                for (int i = tid; i < ns * spw; i += PP_THREADS) {
+                for (int i = tid; i < ns * spw; i += NT) {
                     const int r = (int)__umulhi((uint32_t)i, spw_magic), wc = i - r * spw;
                     const int s = s_done + r, v = s - g.oy;
                     uint32_t* d = (uint32_t*)(S + (size_t)slotS(s) * sp) + wc;
@@ -895,7 +896,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                     const int nq = (nw3 + 15) >> 4;                      // 16-byte items per row
                     const uint32_t nq_magic = (uint32_t)(0xFFFFFFFFu / (uint32_t)max(nq, 2)) + 1u;
                     const int total = ns * nq;
-                    for (int i = tid; i < total; i += PP_THREADS) {
+                    for (int i = tid; i < total; i += NT) {
                         const int r = nq > 1 ? (int)__umulhi((uint32_t)i, nq_magic) : i;
                         const int qc = i - r * nq;
                         const int s = s_done + r, v = s - g.oy;
@@ -939,7 +940,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
                     }
                 } else {            // no H pass: T holds raw rows at byte offset t_off
                     const int total = ns * nw3;
-                    for (int i = tid; i < total; i += PP_THREADS) {
+                    for (int i = tid; i < total; i += NT) {
                         const int r = i / nw3, x = i - r * nw3;
                         const int s = s_done + r, v = s - g.oy;
                         if (v < 0 || v >= nh) continue;
@@ -968,9 +969,9 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         const int cv_done = g.pad1 ? s_done : t_done;
 
         // ================= 2b. general area regime: x-pass of the canvas rows that just became available
-        if (g.regime == REG_GENERAL) {
+        if (P.CX > 0) {
             const int nrow = cv_done - xb_done;
-            for (int i = tid; i < nrow * out; i += PP_THREADS) {
+            for (int i = tid; i < nrow * out; i += NT) {
                 const int r = out > 1 ? (int)__umulhi((uint32_t)i, out_magic) : i;
                 const int dx = i - r * out;
                 const int cr = xb_done + r;
@@ -997,7 +998,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
         int a_new = a_done;
         while (a_new < P.a1 && ar_hi[a_new - P.a0] <= cv_done) a_new++;
         const int npix = (a_new - a_done) * out;
-        for (int i = tid; i < npix; i += PP_THREADS) {
+        for (int i = tid; i < npix; i += NT) {
             const int ar = out > 1 ? (int)__umulhi((uint32_t)i, out_magic) : i;
             const int dx = i - ar * out;
             const int dy = a_done + ar;
@@ -1021,10 +1022,25 @@ __global__ void __launch_bounds__(PP_THREADS, 2) preprocess_kernel(const PPParam
             } else if (g.regime == REG_GENERAL) {
                 const int ny = yt_n[ai];
                 float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+                const int nx = xt_n[dx];
+                const int* xsi = xt_si + dx * xcap;
+                const float* xal = xt_al + dx * xcap;
                 for (int j = 0; j < ny; j++) {
                     const float beta = yt_b[ai * ycap + j];
-                    const float* xr = XB + (size_t)slotX(yt_s[ai * ycap + j]) * xbp + dx * 3;
-                    const float b0 = xr[0], b1 = xr[1], b2 = xr[2];
+                    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                    if (P.CX > 0) {      // x-pass already in the fp32 ring
+                        const float* xr = XB + (size_t)slotX(yt_s[ai * ycap + j]) * xbp + dx * 3;
+                        b0 = xr[0]; b1 = xr[1]; b2 = xr[2];
+                    } else {
+                        const uint8_t* row = CV + (size_t)slotCV(yt_s[ai * ycap + j]) * CVp;
+                        for (int k = 0; k < nx; k++) {
+                            const uint8_t* q = row + xsi[k] * 3;
+                            const float al = xal[k];
+                            b0 = __fadd_rn(b0, __fmul_rn((float)q[0], al));
+                            b1 = __fadd_rn(b1, __fmul_rn((float)q[1], al));
+                            b2 = __fadd_rn(b2, __fmul_rn((float)q[2], al));
+                        }
+                    }
                     if (j == 0) { m0 = __fmul_rn(beta, b0); m1 = __fmul_rn(beta, b1); m2 = __fmul_rn(beta, b2); }
                     else {
                         m0 = __fadd_rn(m0, __fmul_rn(beta, b0)); m1 = __fadd_rn(m1, __fmul_rn(beta, b1)); m2 = __fadd_rn(m2, __fmul_rn(beta, b2));
@@ -1065,7 +1081,7 @@ int launch_preprocess(const PPParams& p, cudaStream_t stream) {
         if (e != cudaSuccess) return PA_ERR_CUDA;
         attr_set = true;
     }
-    preprocess_kernel<<<p.n_crops * PP_SPLIT, PP_THREADS, p.smem_bytes, stream>>>(p);
+    preprocess_kernel<<<p.n_crops * PP_SPLIT, p.threads, p.smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
