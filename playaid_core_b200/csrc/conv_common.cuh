@@ -1,0 +1,160 @@
+// Shared by the tcgen05 convolution kernels (conv_gemm.cu, conv_patch.cu): tile constants and the
+// 16-warp TMEM epilogue.
+#pragma once
+#include "pa_internal.cuh"
+#include "ptx.cuh"
+
+namespace pa {
+
+constexpr int CG_FIRST_EPI_WARP = 2;
+constexpr int CG_EPI_WARPS = 16;
+constexpr int CG_THREADS = (CG_FIRST_EPI_WARP + CG_EPI_WARPS) * 32;  // TMA warp, MMA warp, 16 epilogue warps
+constexpr int CG_BLOCK_M = 128;
+constexpr int CG_BLOCK_K = 64;
+constexpr int CG_A_BYTES = CG_BLOCK_M * CG_BLOCK_K * 2;  // 16 KB
+
+// Epilogue of one CTA: TMEM accumulator -> fp32 scale/shift (folded BN or bias) -> (+ residual) -> (ReLU)
+// -> 16-bit hi (+ lo) planes or fp32. Sixteen warps: four per TMEM lane quarter, each owning every
+// fourth 16-column chunk, so TMEM / global latencies of one warp hide behind the others. One thread per
+// accumulator row (= output pixel); its channels are contiguous in NHWC, so every access is a 32-byte
+// run. The residual of a warp's next chunk is prefetched while the current one is processed.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float a, float b) {
+    if (F16) {
+        const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int BLOCK_N, bool F16, bool SPLIT>
+__device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                         int warp, int lane, int total_tiles) {
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int wq = (warp - CG_FIRST_EPI_WARP) >> 2;  // which of the quarter's four warps
+    const int r = q * 32 + lane;
+    const bool has_res = args.res_hi != nullptr;
+    const bool has_res_lo = args.res_lo != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        const int64_t row = (int64_t)mt * CG_BLOCK_M + r;
+        const bool row_ok = row < args.m_total;
+        const int n_base = nt * BLOCK_N;
+        const int64_t o_base = row * args.cout + n_base;
+        uint4 rh0, rh1, rl0, rl1;  // residual of the current chunk
+        rh0 = rh1 = rl0 = rl1 = make_uint4(0, 0, 0, 0);
+        auto load_res = [&](int c0, uint4& a0, uint4& a1, uint4& b0, uint4& b1) {
+            if (has_res && row_ok && c0 < BLOCK_N && n_base + c0 + 16 <= args.cout) {
+                const uint4* rp = (const uint4*)(args.res_hi + o_base + c0);
+                a0 = __ldg(rp); a1 = __ldg(rp + 1);
+                if (has_res_lo) {
+                    const uint4* lp = (const uint4*)(args.res_lo + o_base + c0);
+                    b0 = __ldg(lp); b1 = __ldg(lp + 1);
+                }
+            }
+        };
+        load_res(wq * 16, rh0, rh1, rl0, rl1);
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = wq * 16; c0 < BLOCK_N; c0 += 64) {
+            float v[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after per-row predication
+            tmem_ld16(t_addr + c0, v);
+            uint4 nh0, nh1, nl0, nl1;
+            nh0 = nh1 = nl0 = nl1 = make_uint4(0, 0, 0, 0);
+            load_res(c0 + 64, nh0, nh1, nl0, nl1);
+            const int n = n_base + c0;
+            if (n < args.cout && row_ok) {
+                const bool full16 = (n + 16 <= args.cout);
+                if (args.scale) {
+                    if (full16) {
+                        const float4* sp4 = (const float4*)(args.scale + n);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { const float4 t = __ldg(sp4 + i); v[4 * i] *= t.x; v[4 * i + 1] *= t.y; v[4 * i + 2] *= t.z; v[4 * i + 3] *= t.w; }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] *= __ldg(args.scale + n + i);
+                    }
+                }
+                if (args.shift) {
+                    if (full16) {
+                        const float4* sp4 = (const float4*)(args.shift + n);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) { const float4 t = __ldg(sp4 + i); v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w; }
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) v[i] += __ldg(args.shift + n + i);
+                    }
+                }
+                if (has_res && full16) {
+                    const uint32_t w[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        v[2 * i] += dec16<F16>((uint16_t)(w[i] & 0xFFFF));
+                        v[2 * i + 1] += dec16<F16>((uint16_t)(w[i] >> 16));
+                    }
+                    if (has_res_lo) {
+                        const uint32_t x[8] = {rl0.x, rl0.y, rl0.z, rl0.w, rl1.x, rl1.y, rl1.z, rl1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            v[2 * i] += dec16<F16>((uint16_t)(x[i] & 0xFFFF));
+                            v[2 * i + 1] += dec16<F16>((uint16_t)(x[i] >> 16));
+                        }
+                    }
+                }
+                if (args.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                const int64_t o = o_base + c0;
+                if (args.out_f32) {
+                    if (full16 && ((o & 3) == 0)) {
+                        float4* op = (float4*)(args.out_f32 + o);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    } else {
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) args.out_f32[o + i] = v[i];
+                    }
+                }
+                if (args.out_hi) {
+                    if (full16 && ((o & 7) == 0)) {
+                        uint32_t h[8], l[8];
+                        if (SPLIT) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) split2<F16>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
+                        }
+                        uint4* op = (uint4*)(args.out_hi + o);
+                        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                        if (SPLIT) {
+                            uint4* lp = (uint4*)(args.out_lo + o);
+                            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                        }
+                    } else {
+                        uint16_t* oh = (uint16_t*)args.out_hi;
+                        uint16_t* ol = (uint16_t*)args.out_lo;
+                        for (int i = 0; i < 16; i++) if (n + i < args.cout) {
+                            const uint16_t h0 = enc16<F16>(v[i]);
+                            oh[o + i] = h0;
+                            if (SPLIT) ol[o + i] = enc16<F16>(v[i] - dec16<F16>(h0));
+                        }
+                    }
+                }
+            }
+            rh0 = nh0; rh1 = nh1; rl0 = nl0; rl1 = nl1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+}
+
+}  // namespace pa

@@ -261,7 +261,8 @@ struct ConvLayer {
 
 struct PlanOp {
     char name[64];
-    int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool
+    int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool, 4 conv 3x3 patch mode
+    int patch_ht; bool patch_wres; size_t patch_smem;
     Conv1Args c1;
     Conv1Maps c1maps;
     ConvMaps maps;
@@ -688,9 +689,20 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     else if (hout == 4) { wt = 4; ht = 4; nt = 8; }
     else if (hout == 1) { wt = 1; ht = 1; nt = 128; }
     else return PA_ERR_UNSUPPORTED;
+    // stride-1 3x3 layers on full-width tiles: patch staging (one box of ht+2 rows per horizontal shift)
+    bool patch = (L.k == 3 && L.stride == 1 && L.pad == 1 && (hout == 32 || hout == 16) && n_b == 1 && (L.cin % 64) == 0 &&
+                  L.cout == L.block_n && getenv("PA_NO_PATCH") == nullptr);
+    int patch_stages = 0;
+    if (patch) {
+        patch_stages = conv_patch_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
+        if (patch_stages < 2) patch = false;
+    }
     for (int pl = 0; pl < n_a; pl++) {
         const bf16* base = pl == 0 ? in.hi : in.lo;
-        if (L.stride == 1) {
+        if (patch) {
+            int rc = make_map_a(ctx, &op.maps.a[pl][0], base, L.cin, L.hin, L.hin, N, 1, 0, 0, wt, ht + 2, nt);
+            if (rc != PA_OK) return rc;
+        } else if (L.stride == 1) {
             int rc = make_map_a(ctx, &op.maps.a[pl][0], base, L.cin, L.hin, L.hin, N, 1, 0, 0, wt, ht, nt);
             if (rc != PA_OK) return rc;
         } else {
@@ -714,8 +726,9 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.k_per_tap = L.cin;
     a.ho = hout; a.wo = hout;
     op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
-    a.num_stages = conv_gemm_pick_stages(L.block_n, n_a, n_b);
+    a.num_stages = patch ? patch_stages : conv_gemm_pick_stages(L.block_n, n_a, n_b);
     if (a.num_stages < 2) return PA_ERR_UNSUPPORTED;
+    if (patch) { op.kind = 4; op.patch_ht = ht; }
     a.scale = L.scale; a.shift = L.shift;
     a.res_hi = res ? res->hi : nullptr;
     a.res_lo = res ? res->lo : nullptr;
@@ -818,6 +831,7 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
             case 0: rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, st); break;
             case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
             case 2: rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st); break;
+            case 4: rc = launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, st); break;
             case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
         }
         if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "feature kernel launch") : rc;
@@ -904,7 +918,9 @@ extern "C" int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int 
         out.hi = (bf16*)out_hi; out.lo = (bf16*)out_lo;
         PlanOp op;
         rc = plan_conv(&m, L, in, n, res_hi ? &res : nullptr, out_hi ? &out : nullptr, out_f32, op);
-        if (rc == PA_OK) rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, (cudaStream_t)stream);
+        if (rc == PA_OK) rc = (op.kind == 4)
+            ? launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, (cudaStream_t)stream)
+            : launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, (cudaStream_t)stream);
         if (rc == PA_OK) {
             ctx->launches += 1;
             cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);

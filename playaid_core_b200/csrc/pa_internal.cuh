@@ -70,6 +70,10 @@ struct ConvArgs {
 int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms,
                      cudaStream_t stream);
 size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages);
+// 3x3 / stride-1 layers on full-width tiles: patch staging (conv_patch.cu)
+int conv_patch_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
+int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
+                      int num_sms, cudaStream_t stream);
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b);
 
 // ---------------------------------------------------------------- conv1 (7x7 stride 2, TMA im2col)
