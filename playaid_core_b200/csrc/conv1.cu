@@ -64,33 +64,38 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            // weights once: 7 boxes [32 k, 64 cout] per plane
-            mbar_arrive_expect_tx(bfull, NB * C1_B_PLANE);
-            for (int pl = 0; pl < NB; pl++)
-                for (int ky = 0; ky < 7; ky++) tma_load_2d(sB + pl * C1_B_PLANE + ky * C1_B_KY, &maps.b[pl], bfull, ky * 32, 0);
+        // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
+        {
+            if (elect_one()) {   // weights once: 7 boxes [32 k, 64 cout] per plane
+                mbar_arrive_expect_tx(bfull, NB * C1_B_PLANE);
+                for (int pl = 0; pl < NB; pl++)
+                    for (int ky = 0; ky < 7; ky++) tma_load_2d(sB + pl * C1_B_PLANE + ky * C1_B_KY, &maps.b[pl], bfull, ky * 32, 0);
+            }
+            __syncwarp();
             int st = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n = tile >> 5, oy0 = (tile & 31) << 1;
                 mbar_wait(&aempty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
 #pragma unroll
-                for (int pl = 0; pl < NA; pl++) {
+                    for (int pl = 0; pl < NA; pl++) {
 #pragma unroll
-                    for (int ky = 0; ky < 7; ky++) {
-                        const int dy = ky - 3;           // input row = 2*oy + dy
-                        const int py = dy & 1;           // row parity -> which tensor map
-                        const int j0 = oy0 + (dy - py) / 2;
-                        tma_load_4d(sA + st * STAGE_BYTES + pl * C1_A_PLANE + ky * C1_A_KY, &maps.a[pl][py], &afull[st], 0, 0, j0, n);
+                        for (int ky = 0; ky < 7; ky++) {
+                            const int dy = ky - 3;           // input row = 2*oy + dy
+                            const int py = dy & 1;           // row parity -> which tensor map
+                            const int j0 = oy0 + (dy - py) / 2;
+                            tma_load_4d(sA + st * STAGE_BYTES + pl * C1_A_PLANE + ky * C1_A_KY, &maps.a[pl][py], &afull[st], 0, 0, j0, n);
+                        }
                     }
                 }
+                __syncwarp();
                 if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp walks the loop; one elected lane issues) =====
+        {
             const uint32_t idesc = a.f16 ? umma_idesc_f16(128, C1_COUT) : umma_idesc_bf16(128, C1_COUT);
             const uint32_t sb0 = smem_u32(sB);
             mbar_wait(bfull, 0);
@@ -104,18 +109,22 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C1_COUT;
                 const uint32_t sa0 = smem_u32(sA + st * STAGE_BYTES);
+                if (elect_one()) {
+                    const uint64_t da0 = umma_desc_sw64(sa0), db0 = umma_desc_sw64(sb0);
+                    const uint64_t dal0 = (NA == 2) ? umma_desc_sw64(sa0 + C1_A_PLANE) : 0;
+                    const uint64_t dbl0 = (NB == 2) ? umma_desc_sw64(sb0 + C1_B_PLANE) : 0;
 #pragma unroll
-                for (int ks = 0; ks < 14; ks++) {
-                    const uint32_t koff_a = (ks >> 1) * C1_A_KY + (ks & 1) * 32;
-                    const uint32_t koff_b = (ks >> 1) * C1_B_KY + (ks & 1) * 32;
-                    const uint64_t da = umma_desc_sw64(sa0 + koff_a);
-                    const uint64_t db = umma_desc_sw64(sb0 + koff_b);
-                    umma_bf16(d_tmem, da, db, idesc, ks != 0);
-                    if (NA == 2) umma_bf16(d_tmem, umma_desc_sw64(sa0 + C1_A_PLANE + koff_a), db, idesc, 1);
-                    if (NB == 2) umma_bf16(d_tmem, da, umma_desc_sw64(sb0 + C1_B_PLANE + koff_b), idesc, 1);
+                    for (int ks = 0; ks < 14; ks++) {
+                        const uint32_t ia = ((ks >> 1) * C1_A_KY + (ks & 1) * 32) >> 4;   // start-address field increments
+                        const uint32_t ib = ((ks >> 1) * C1_B_KY + (ks & 1) * 32) >> 4;
+                        umma_bf16(d_tmem, da0 + ia, db0 + ib, idesc, ks != 0);
+                        if (NA == 2) umma_bf16(d_tmem, dal0 + ia, db0 + ib, idesc, 1);
+                        if (NB == 2) umma_bf16(d_tmem, da0 + ia, dbl0 + ib, idesc, 1);
+                    }
+                    umma_commit(&aempty[st]);
+                    umma_commit(&tfull[acc]);
                 }
-                umma_commit(&aempty[st]);
-                umma_commit(&tfull[acc]);
+                __syncwarp();
                 if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }

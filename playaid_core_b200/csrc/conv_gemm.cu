@@ -71,8 +71,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
+        {
             int st = 0; uint32_t ph = 0;
             const int pix_per_img = args.ho * args.wo;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -95,21 +95,24 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
                         uint8_t* sb = sa + NA * CG_A_BYTES;
-                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
 #pragma unroll
-                        for (int pl = 0; pl < NA; pl++)
-                            tma_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
+                            for (int pl = 0; pl < NA; pl++)
+                                tma_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
 #pragma unroll
-                        for (int pl = 0; pl < NB; pl++)
-                            tma_load_2d(sb + pl * B_BYTES, &maps.b[pl], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                            for (int pl = 0; pl < NB; pl++)
+                                tma_load_2d(sb + pl * B_BYTES, &maps.b[pl], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                        }
+                        __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp walks the loop; one elected lane issues) =====
+        {
             const uint32_t idesc = args.f16 ? umma_idesc_f16(CG_BLOCK_M, BLOCK_N) : umma_idesc_bf16(CG_BLOCK_M, BLOCK_N);
             int st = 0; uint32_t ph = 0;
             int it = 0;
@@ -124,18 +127,24 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
                     const uint32_t sb = sa + NA * CG_A_BYTES;
+                    if (elect_one()) {
+                        // descriptors differ only in the 14-bit start-address field: add 32 B >> 4 per k-step
+                        const uint64_t da0 = umma_desc_sw128(sa), db0 = umma_desc_sw128(sb);
+                        const uint64_t dal0 = (NA == 2) ? umma_desc_sw128(sa + CG_A_BYTES) : 0;
+                        const uint64_t dbl0 = (NB == 2) ? umma_desc_sw128(sb + B_BYTES) : 0;
 #pragma unroll
-                    for (int k = 0; k < CG_BLOCK_K / 16; k++) {
-                        const uint64_t da = umma_desc_sw128(sa + k * 32);
-                        const uint64_t db = umma_desc_sw128(sb + k * 32);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
-                        if (NA == 2) umma_bf16(d_tmem, umma_desc_sw128(sa + CG_A_BYTES + k * 32), db, idesc, 1);
-                        if (NB == 2) umma_bf16(d_tmem, da, umma_desc_sw128(sb + B_BYTES + k * 32), idesc, 1);
+                        for (int k = 0; k < CG_BLOCK_K / 16; k++) {
+                            umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                            if (NA == 2) umma_bf16(d_tmem, dal0 + 2 * k, db0 + 2 * k, idesc, 1);
+                            if (NB == 2) umma_bf16(d_tmem, da0 + 2 * k, dbl0 + 2 * k, idesc, 1);
+                        }
+                        umma_commit(&empty[st]);
                     }
-                    umma_commit(&empty[st]);
+                    __syncwarp();
                     if (++st == S) { st = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
             }
         }
     } else {

@@ -60,14 +60,15 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            if (WRES) {
+        // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
+        {
+            if (WRES && elect_one()) {
                 mbar_arrive_expect_tx(wfull, wres_bytes);
                 for (int tap = 0; tap < 9; tap++)
                     for (int kc = 0; kc < kb; kc++)
                         tma_load_2d(wres + (size_t)(tap * kb + kc) * B_BYTES, &maps.b[0], wfull, tap * args.k_per_tap + kc * CG_BLOCK_K, 0);
             }
+            __syncwarp();
             int st = 0; uint32_t ph = 0;
             const int pix_per_img = args.ho * args.wo;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -78,24 +79,27 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = stages + (size_t)st * stage_bytes;
-                        mbar_arrive_expect_tx(&full[st], stage_bytes);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&full[st], stage_bytes);
 #pragma unroll
-                        for (int pl = 0; pl < NA; pl++)
-                            tma_load_4d(sa + pl * pg.patch_bytes, &maps.a[pl][0], &full[st], kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
-                        if (!WRES) {
-                            uint8_t* sb = sa + NA * pg.patch_bytes;
+                            for (int pl = 0; pl < NA; pl++)
+                                tma_load_4d(sa + pl * pg.patch_bytes, &maps.a[pl][0], &full[st], kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
+                            if (!WRES) {
+                                uint8_t* sb = sa + NA * pg.patch_bytes;
 #pragma unroll
-                            for (int dy = 0; dy < 3; dy++)
-                                tma_load_2d(sb + dy * B_BYTES, &maps.b[0], &full[st], (dy * 3 + dxi) * args.k_per_tap + kc * CG_BLOCK_K, 0);
+                                for (int dy = 0; dy < 3; dy++)
+                                    tma_load_2d(sb + dy * B_BYTES, &maps.b[0], &full[st], (dy * 3 + dxi) * args.k_per_tap + kc * CG_BLOCK_K, 0);
+                            }
                         }
+                        __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp walks the loop; one elected lane issues) =====
+        {
             const uint32_t idesc = args.f16 ? umma_idesc_f16(CG_BLOCK_M, BLOCK_N) : umma_idesc_bf16(CG_BLOCK_M, BLOCK_N);
             if (WRES) { mbar_wait(wfull, 0); tc_fence_after(); }
             const uint32_t wres_u = smem_u32(wres);
@@ -114,23 +118,29 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
                         tc_fence_after();
                         const uint32_t sa = smem_u32(stages + (size_t)st * stage_bytes);
                         const uint32_t sb = sa + NA * pg.patch_bytes;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int dy = 0; dy < 3; dy++) {
-                            const uint32_t a0 = sa + dy * pg.row_bytes;
-                            const uint32_t b0 = WRES ? wres_u + (uint32_t)(((dy * 3 + dxi) * kb + kc) * B_BYTES) : sb + dy * B_BYTES;
+                            for (int dy = 0; dy < 3; dy++) {
+                                const uint32_t a0 = sa + dy * pg.row_bytes;
+                                const uint32_t b0 = WRES ? wres_u + (uint32_t)(((dy * 3 + dxi) * kb + kc) * B_BYTES) : sb + dy * B_BYTES;
+                                // descriptors differ only in the 14-bit start-address field: add 32 B >> 4 per k-step
+                                const uint64_t da0 = umma_desc_sw128(a0), db0 = umma_desc_sw128(b0);
+                                const uint64_t dl0 = (NA == 2) ? umma_desc_sw128(a0 + pg.patch_bytes) : 0;
 #pragma unroll
-                            for (int k = 0; k < CG_BLOCK_K / 16; k++) {
-                                const uint64_t db = umma_desc_sw128(b0 + k * 32);
-                                umma_bf16(d_tmem, umma_desc_sw128(a0 + k * 32), db, idesc, first ? 0u : 1u);
-                                first = 0;
-                                if (NA == 2) umma_bf16(d_tmem, umma_desc_sw128(a0 + pg.patch_bytes + k * 32), db, idesc, 1);
+                                for (int k = 0; k < CG_BLOCK_K / 16; k++) {
+                                    umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, first ? 0u : 1u);
+                                    first = 0;
+                                    if (NA == 2) umma_bf16(d_tmem, dl0 + 2 * k, db0 + 2 * k, idesc, 1);
+                                }
                             }
+                            umma_commit(&empty[st]);
                         }
-                        umma_commit(&empty[st]);
+                        __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
             }
         }
     } else {
