@@ -142,7 +142,8 @@ int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, 
 /*
  * Single layers (synchronous; scratch allocated and freed inside): one convolution as a tcgen05
  * implicit GEMM on NHWC bf16 activations [n][hin][hin][cin] (cin % 64 == 0, hin in {32,16,8,4,1} for
- * the output), and the 7x7/s2 stem on NHWC4 crops. Weights / scale / shift are host fp32 in PyTorch
+ * the output), and the fused stem (7x7/s2 conv + scale/shift + ReLU + 3x3/s2 max-pool) on NHWC4P crops
+ * [n][128][136][4] -> [n][32][32][64]. Weights / scale / shift are host fp32 in PyTorch
  * layout; y = conv(x, w) * scale + shift (+ residual) (ReLU). These are the building blocks
  * pa_features sequences; exposed for layer-level parity tests against torch.nn.functional.conv2d.
  * in_lo / out_lo / res_lo may be NULL (no split). split_w is a flag word: bit 0 = split the weights

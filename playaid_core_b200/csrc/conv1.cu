@@ -12,9 +12,11 @@
 // of a tensor map over every other input row (one map per row parity); rows above/below the image
 // are zero-filled by the TMA unit, columns by the padding in memory. Seven 8 KB boxes per tile land
 // in K-major SWIZZLE_64B tiles, 14 tcgen05.mma (M=128, N=64, K=16) accumulate in TMEM
-// (double-buffered), four epilogue warps apply scale/shift + ReLU and store NHWC.
+// (double-buffered). The epilogue (16 warps) applies scale/shift + ReLU and FUSES the 3x3/s2 max-pool: a CTA
+// walks the 32 tiles of a crop in order, keeps the last three conv rows in shared memory (fp32) and emits one
+// pooled row [32 x 64] per tile -- the 64x64x64 stem output never touches HBM.
 //
-// Replaces resnet18.conv1/bn1/relu (torchvision, via playaid/models/cnn_action_detector.py:16,32).
+// Replaces resnet18.conv1/bn1/relu/maxpool (torchvision, via playaid/models/cnn_action_detector.py:16,32).
 #include "pa_internal.cuh"
 #include "ptx.cuh"
 
@@ -27,16 +29,19 @@ constexpr int C1_A_PLANE = 7 * C1_A_KY;    // 56 KB
 constexpr int C1_B_KY = 64 * 64;           // 64 cout rows x 64 B
 constexpr int C1_B_PLANE = 7 * C1_B_KY;    // 28 KB
 constexpr int C1_COUT = 64;
+constexpr int C1_ROW_PITCH = 68;                              // floats per pixel in the pooling buffer (64 + 4: bank spread)
+constexpr int C1_ROWS_BYTES = 3 * 64 * C1_ROW_PITCH * 4;      // three conv rows, fp32
 
 template <int NA, int NB>
 __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int NSTAGE = (NA == 1) ? 3 : 1;
+    constexpr int NSTAGE = (NA == 1) ? 2 : 1;
     constexpr int STAGE_BYTES = NA * C1_A_PLANE;
     uint8_t* sA = smem;                                    // [NSTAGE][NA][7][128 x 64 B]
     uint8_t* sB = smem + NSTAGE * STAGE_BYTES;             // [NB][7][64 x 64 B]
-    uint64_t* bars = (uint64_t*)(sB + NB * C1_B_PLANE);
+    float* rows = (float*)(sB + NB * C1_B_PLANE);          // [3][64 px][C1_ROW_PITCH] conv rows for the fused max-pool
+    uint64_t* bars = (uint64_t*)((uint8_t*)rows + C1_ROWS_BYTES);
     uint64_t* afull = bars;          // [NSTAGE]
     uint64_t* aempty = bars + 3;     // [NSTAGE]
     uint64_t* tfull = bars + 6;      // [2]
@@ -45,7 +50,6 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
     uint32_t* tmem_slot = (uint32_t*)(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = a.n_crops * 32;
 
     if (warp == 0 && lane == 0) {
         for (int pl = 0; pl < NA; pl++) { tma_prefetch_desc(&maps.a[pl][0]); tma_prefetch_desc(&maps.a[pl][1]); }
@@ -73,8 +77,9 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
             }
             __syncwarp();
             int st = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n = tile >> 5, oy0 = (tile & 31) << 1;
+            for (int n = blockIdx.x; n < a.n_crops; n += gridDim.x)
+            for (int t = 0; t < 32; t++) {   // a CTA walks the tiles of a crop in order (the fused max-pool needs it)
+                const int oy0 = t << 1;
                 mbar_wait(&aempty[st], ph ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
@@ -101,7 +106,8 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
             mbar_wait(bfull, 0);
             int st = 0; uint32_t ph = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+            for (int n = blockIdx.x; n < a.n_crops; n += gridDim.x)
+            for (int t = 0; t < 32; t++, it++) {
                 const int acc = it & 1;
                 const uint32_t acc_ph = (it >> 1) & 1;
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
@@ -136,13 +142,15 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
         float sc[16], sh[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) { sc[i] = __ldg(a.scale + c0 + i); sh[i] = __ldg(a.shift + c0 + i); }
+        const int et = threadIdx.x - 64;           // 0..511 among the epilogue threads
+        const int ppx = et >> 4, pcg = (et & 15) * 4; // pooling role: pooled column, first of 4 channels
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        for (int n = blockIdx.x; n < a.n_crops; n += gridDim.x)
+        for (int t = 0; t < 32; t++, it++) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             mbar_wait(&tfull[acc], acc_ph);
             tc_fence_after();
-            const int64_t o = ((int64_t)tile * 128 + r) * C1_COUT + c0;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C1_COUT + c0;
             float v[16];
             tmem_ld16(t_addr, v);
@@ -151,31 +159,35 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
             if (lane == 0) mbar_arrive(&tempty[acc]);   // accumulator drained into registers: release it early
 #pragma unroll
             for (int i = 0; i < 16; i++) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
-            uint32_t h[8], l[8];
-            if (a.out_lo) {
-                if (a.f16) {
+            // conv row (2t + r/64), column r%64 -> pooling buffer slot (row % 3)
+            {
+                const int crow = 2 * t + (r >> 6);
+                float4* d = (float4*)(rows + ((size_t)(crow % 3) * 64 + (r & 63)) * C1_ROW_PITCH + c0);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) split2<true>(v[2 * i], v[2 * i + 1], h[i], l[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) split2<false>(v[2 * i], v[2 * i + 1], h[i], l[i]);
-                }
-                uint4* lp = (uint4*)(a.out_lo + o);
-                lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
-                lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
-            } else if (a.f16) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const __half2 t = __floats2half2_rn(fminf(v[2 * i], 65504.f), fminf(v[2 * i + 1], 65504.f));
-                    h[i] = *reinterpret_cast<const uint32_t*>(&t);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                for (int i = 0; i < 4; i++) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            uint4* op = (uint4*)(a.out_hi + o);
-            op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // both conv rows of the tile are in shared memory
+            // pooled row t: max over conv rows 2t-1..2t+1 and columns 2px-1..2px+1 (inputs are >= 0 after ReLU)
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++) {
+                const int crow = 2 * t + dr;
+                if (crow < 0) continue;
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    const int col = 2 * ppx + dc;
+                    if (col < 0) continue;
+                    const float4 x = *(const float4*)(rows + ((size_t)(crow % 3) * 64 + col) * C1_ROW_PITCH + pcg);
+                    m.x = fmaxf(m.x, x.x); m.y = fmaxf(m.y, x.y); m.z = fmaxf(m.z, x.z); m.w = fmaxf(m.w, x.w);
+                }
+            }
+            const int64_t o = (((int64_t)n * 32 + t) * 32 + ppx) * C1_COUT + pcg;
+            uint32_t h0, h1, l0, l1;
+            if (a.f16) { split2<true>(m.x, m.y, h0, l0); split2<true>(m.z, m.w, h1, l1); }
+            else { split2<false>(m.x, m.y, h0, l0); split2<false>(m.z, m.w, h1, l1); }
+            *(uint2*)(a.out_hi + o) = make_uint2(h0, h1);
+            if (a.out_lo) *(uint2*)(a.out_lo + o) = make_uint2(l0, l1);
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // pooling done before the next tile reuses a slot
         }
     }
     tc_fence_before();
@@ -186,14 +198,14 @@ __global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_const
 template <int NA, int NB>
 static int launch_c1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream) {
     auto kern = conv1_kernel<NA, NB>;
-    constexpr int NSTAGE = (NA == 1) ? 3 : 1;
-    const size_t smem = 1024 + (size_t)NSTAGE * NA * C1_A_PLANE + (size_t)NB * C1_B_PLANE + 128;
+    constexpr int NSTAGE = (NA == 1) ? 2 : 1;
+    const size_t smem = 1024 + (size_t)NSTAGE * NA * C1_A_PLANE + (size_t)NB * C1_B_PLANE + C1_ROWS_BYTES + 128;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PA_ERR_CUDA;
         attr_set = true;
     }
-    int grid = a.n_crops * 32;
+    int grid = a.n_crops;   // whole crops per CTA
     if (grid > num_sms) grid = num_sms;
     kern<<<grid, C1_THREADS, smem, stream>>>(maps, a);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;

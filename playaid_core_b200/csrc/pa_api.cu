@@ -568,14 +568,13 @@ extern "C" int pa_model_finalize(pa_model* m, int precision) {
 
 extern "C" int pa_model_precision(const pa_model* m) { return m ? m->precision : -1; }
 
-// activation arena: one big buffer (stem output) + four small ones, per plane
-static const size_t kBigElems = (size_t)64 * 64 * 64;    // per crop
+// activation arena: four [n][32][32][64]-sized buffers (the stem kernel emits the pooled map directly), per plane
 static const size_t kSmallElems = (size_t)32 * 32 * 64;  // per crop
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static size_t features_ws_bytes(const pa_model* m, int n) {
     const int planes = prec_split(m->precision) ? 2 : 1;
-    size_t per_plane = align256(kBigElems * n * 2) + 4 * align256(kSmallElems * n * 2) + align256((size_t)n * 512 * 2);
+    size_t per_plane = 4 * align256(kSmallElems * n * 2) + align256((size_t)n * 512 * 2);
     return per_plane * planes + 1024;
 }
 static size_t head_ws_bytes(const pa_model* m, int n_feat) {
@@ -647,7 +646,7 @@ static int plan_stem(pa_ctx* ctx, PlanOp& op, const bf16* in_hi, const bf16* in_
                      const float* scale, const float* shift, bf16* out_hi, bf16* out_lo, int n, int f16) {
     memset(&op, 0, sizeof(op));
     op.kind = 0;
-    snprintf(op.name, sizeof(op.name), "conv1_stem");
+    snprintf(op.name, sizeof(op.name), "conv1_stem+maxpool");
     for (int py = 0; py < 2; py++) {
         int rc = make_map_c1a(ctx, &op.c1maps.a[0][py], in_hi, n, py);
         if (rc != PA_OK) return rc;
@@ -751,7 +750,6 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         if (split) { a.lo = (bf16*)p; p += align256(elems * 2); }
         return a;
     };
-    Act big = carve(kBigElems * n);
     Act sm[4];
     for (int i = 0; i < 4; i++) sm[i] = carve(kSmallElems * n);
     Act pooled = carve((size_t)n * 512);
@@ -761,17 +759,9 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         PlanOp op;
         const bf16* in_hi = (const bf16*)crops;
         const bf16* in_lo = split ? in_hi + (size_t)n * 128 * 136 * 4 : nullptr;
-        int rc = plan_stem(m->ctx, op, in_hi, in_lo, m->stem_w_hi, m->stem_w_lo, m->stem.scale, m->stem.shift, big.hi, big.lo, n, f16);
+        int rc = plan_stem(m->ctx, op, in_hi, in_lo, m->stem_w_hi, m->stem_w_lo, m->stem.scale, m->stem.shift, sm[0].hi, sm[0].lo, n, f16);
         if (rc != PA_OK) return rc;
-        m->plan.push_back(op);
-    }
-    {
-        PlanOp op; memset(&op, 0, sizeof(op));
-        op.kind = 1;
-        snprintf(op.name, sizeof(op.name), "maxpool");
-        op.pin_hi = big.hi; op.pin_lo = big.lo; op.pout_hi = sm[0].hi; op.pout_lo = sm[0].lo;
-        op.pn = n; op.ph = 64; op.pw = 64; op.pc = 64; op.pf16 = f16;
-        m->plan.push_back(op);
+        m->plan.push_back(op);   // conv1 + BN + ReLU + max-pool in one kernel
     }
     int x = 0;  // index of the buffer holding the block input
     size_t ci = 0;

@@ -84,7 +84,7 @@ struct Conv1Maps {
 struct Conv1Args {
     const float* scale;   // [64]
     const float* shift;   // [64]
-    bf16* out_hi;         // [n][64][64][64]
+    bf16* out_hi;         // [n][32][32][64]: conv + BN + ReLU + 3x3/s2 max-pool
     bf16* out_lo;         // or nullptr
     int n_crops;
     int f16;              // 0 bf16, 1 IEEE half

@@ -191,7 +191,7 @@ def test_stem_vs_torch(env, split, half):
     x4[:, :, 4:132, :3] = x.permute(0, 2, 3, 1)
     hi = x4.to(dt)
     lo = (x4 - hi.float()).to(dt) if split else None
-    out_hi = torch.full((N, 64, 64, 64), float("nan"), device="cuda", dtype=dt)
+    out_hi = torch.full((N, 32, 32, 64), float("nan"), device="cuda", dtype=dt)   # conv+BN+ReLU+maxpool fused
     out_lo = torch.zeros_like(out_hi) if split else None
     wc, sc, sh = w.cpu().contiguous(), scale.cpu().contiguous(), shift.cpu().contiguous()  # keep alive across the call
     rc = ctx.lib.pa_stem(ctx.handle, _ptr(hi), _ptr(lo), N, wc.data_ptr(), sc.data_ptr(), sh.data_ptr(), _ptr(out_hi),
@@ -199,7 +199,7 @@ def test_stem_vs_torch(env, split, half):
     _lib.check(rc, ctx.handle, "pa_stem")
     torch.cuda.synchronize()
     y = (out_hi.float() + (out_lo.float() if split else 0)).permute(0, 3, 1, 2)
-    ref = _ref(torch, x, w, 2, 3, scale, shift, relu=True)
+    ref = torch.nn.functional.max_pool2d(_ref(torch, x, w, 2, 3, scale, shift, relu=True), 3, 2, 1)
     err = float((y - ref).abs().max()) / float(ref.abs().max())
     tol = (1e-5 if half else 5e-5) if split else (1e-3 if half else 1e-2)
     assert torch.isfinite(y).all() and err < tol, err
