@@ -100,6 +100,20 @@ int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W
                   int out_layout, int32_t* status, void* stream);
 
 /*
+ * Frames in PINNED HOST memory (what a decoder thread hands over): instead of copying whole frames to
+ * the device, pull only the bytes pa_preprocess will read -- the clipped window rows of every crop,
+ * widened to 16-byte chunks -- over PCIe into `dev_frames`, a device buffer with the same pitch and
+ * frame stride (bytes outside the windows are left untouched and never read). Run it on a side stream
+ * so the transfer of one batch overlaps the kernels of the previous one, then hand `dev_frames` to
+ * pa_preprocess with the same boxes. record.frame - frame_base indexes the batch, so the match's
+ * full record table can be passed without rewriting it per batch. Stands where the reference
+ * hands each decoded numpy frame to square_crop (gen_gt_action_detection.py:38-56, ai_runner.py:440-452).
+ */
+int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_frames, int H, int W, int64_t pitch_bytes,
+                     int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int padding, int frame_base,
+                     uint8_t* dev_frames, void* stream);
+
+/*
  * Classifier. Replaces CNNActionDetector / SpatialStreamCNN forward
  * (playaid/models/cnn_action_detector.py:13-43,86-92) and the argmax / exp head of
  * AIRunner.action_recognition (playaid/ai_runner.py:472-477).

@@ -25,7 +25,7 @@ from . import _lib
 from .dataset_utils import window_index_table
 from .fighter import YoloCrop, boxes_from_timeline
 from .models.cnn_action_detector import CNNActionDetector
-from .preprocess import crop_records, preprocess_crops
+from .preprocess import crop_records, preprocess_crops, stage_windows
 
 
 class MatchStream:
@@ -71,13 +71,18 @@ class MatchStream:
         self.win_rows = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(dev)  # [n_own, F, S]
 
     def push(self, frames: torch.Tensor) -> tuple[int, int]:
-        """frames uint8 CUDA [n,H,W,3]: local frames [pushed, pushed+n). Returns the [a, b) range of own
-        frames (indices into `label`) classified by this call; labels trail the pushed frames by the
-        window reach until the last frame arrives."""
+        """frames uint8 [n,H,W,3], CUDA or pinned host: local frames [pushed, pushed+n). Returns the [a, b)
+        range of own frames (indices into `label`) classified by this call; labels trail the pushed
+        frames by the window reach until the last frame arrives. Pinned host frames are not copied
+        whole: their crop windows are staged into HBM on the detector's copy stream (overlapping the
+        kernels of the previous chunk), or read in place over PCIe when `det.host_mode == "inplace"`."""
         det = self.det
         n = int(frames.shape[0])
         f0 = self.pushed
         assert f0 + n <= self.N
+        slot = None
+        if not frames.is_cuda and det.host_mode == "stage" and frames.is_contiguous():
+            frames, slot = det._stage(frames, self.rec[f0 * self.F : (f0 + n) * self.F], f0)
         rec = self.rec[f0 * self.F : (f0 + n) * self.F].clone()
         rec[:, 0] -= f0  # frame index relative to this chunk
         crops, _ = preprocess_crops(
@@ -85,6 +90,8 @@ class MatchStream:
             dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4P, out=det._crop_buffer(n * self.F),
             status=self.status[f0 : f0 + n].view(-1),
         )
+        if slot is not None:
+            det._stage_release(slot)
         det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
         self.pushed = f0 + n
         return self._label_ready()
@@ -127,6 +134,32 @@ class ActionDetector:
         self.min_frame = min_frame
         self.mean, self.std = tuple(mean), tuple(std)
         self._crops: torch.Tensor | None = None
+        # pinned-host frames: "stage" = pa_stage_windows on a copy stream into one of two HBM frame buffers,
+        # "inplace" = the preprocess kernel reads the pinned memory itself
+        self.host_mode = "stage"
+        self._stage_bufs: list[torch.Tensor] | None = None
+        self._stage_i = 0
+
+    def _stage(self, host_frames: torch.Tensor, rec: torch.Tensor, frame_base: int):
+        dev = self.model._device
+        if self._stage_bufs is None or self._stage_bufs[0].shape[1:] != host_frames.shape[1:] or self._stage_bufs[0].shape[0] < host_frames.shape[0]:
+            self._stage_bufs = [torch.empty(tuple(host_frames.shape), dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+        slot = self._stage_i & 1
+        self._stage_i += 1
+        buf = self._stage_bufs[slot][: host_frames.shape[0]]
+        main = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_event(self._stage_free[slot])   # the kernels that read this buffer two chunks ago are done
+        with torch.cuda.stream(self._copy_stream):
+            stage_windows(host_frames, rec, buf, self.padding, frame_base)
+            self._stage_ready[slot].record(self._copy_stream)
+        main.wait_event(self._stage_ready[slot])
+        return buf, slot
+
+    def _stage_release(self, slot: int) -> None:
+        self._stage_free[slot].record(torch.cuda.current_stream(self.model._device))
 
     def _crop_buffer(self, n: int) -> torch.Tensor:
         planes = 2 if self.model.split else 1

@@ -149,6 +149,24 @@ extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
 extern "C" int64_t pa_launch_count(pa_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ preprocess
+extern "C" int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_frames, int H, int W, int64_t pitch_bytes,
+                                int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int padding, int frame_base,
+                                uint8_t* dev_frames, void* stream) {
+    if (!ctx || !host_frames || !dev_frames || !boxes || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0 || padding < 0)
+        return PA_ERR_INVALID_ARG;
+    if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
+    if (n_crops == 0) return PA_OK;
+    StageParams p;
+    p.src = host_frames; p.dst = dev_frames;
+    p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
+    p.n_frames = n_frames; p.H = H; p.W = W; p.pitch = pitch_bytes; p.fstride = frame_stride_bytes;
+    p.boxes = boxes; p.n_crops = n_crops; p.padding = padding; p.frame_base = frame_base;
+    ProfSpan sp(ctx, "stage_windows", (cudaStream_t)stream);
+    if (launch_stage_windows(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "stage_windows launch");
+    ctx->launches += 1;
+    return PA_OK;
+}
+
 extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, int64_t pitch_bytes,
                              int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,
                              int swap_rb, const float* mean3, const float* std3, void* out, int out_dtype,

@@ -36,6 +36,16 @@ struct PPParams {
     int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
+struct StageParams {
+    const uint8_t* src;     // pinned host frames (device-visible)
+    uint8_t* dst;           // device frame batch with the same pitch / frame stride
+    int64_t frames_bytes;
+    int n_frames, H, W;
+    int64_t pitch, fstride;
+    const int32_t* boxes;   // crop records; record.frame - frame_base indexes the batch
+    int n_crops, padding, frame_base;
+};
+int launch_stage_windows(const StageParams& p, cudaStream_t stream);
 int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);
 size_t preprocess_geom_bytes();
 

@@ -86,6 +86,27 @@ def preprocess_crops(
     return out, status
 
 
+def stage_windows(host_frames: torch.Tensor, records: torch.Tensor, dev_frames: torch.Tensor, padding: int = 30,
+                  frame_base: int = 0) -> None:
+    """`pa_stage_windows` on the current stream: copy the window rows of `records` (int32 CUDA [n,8], frame index
+    = record.frame - frame_base) from pinned host `host_frames` into `dev_frames` (same shape / strides)."""
+    if not host_frames.is_pinned() or not dev_frames.is_cuda or not records.is_cuda:
+        raise _lib.PlayaidLibraryError("stage_windows needs pinned host frames, a CUDA frame buffer and CUDA records")
+    if host_frames.dtype != torch.uint8 or host_frames.shape != dev_frames.shape or host_frames.stride() != dev_frames.stride():
+        raise ValueError("host and device frame batches must have identical uint8 geometry")
+    if host_frames.ndim != 4 or host_frames.shape[3] != 3 or host_frames.stride(3) != 1 or host_frames.stride(2) != 3:
+        raise ValueError("frames must be uint8 [N,H,W,3] with packed pixels")
+    dev = records.device
+    ctx = _lib.Context.get(dev)
+    N, H, W, _ = host_frames.shape
+    fstride = host_frames.stride(0) if N > 1 else host_frames.stride(1) * H
+    with torch.cuda.device(dev):
+        rc = ctx.lib.pa_stage_windows(ctx.handle, host_frames.data_ptr(), N, H, W, host_frames.stride(1), fstride,
+                                      records.data_ptr(), int(records.shape[0]), padding, frame_base,
+                                      dev_frames.data_ptr(), _lib.current_stream_ptr(dev))
+    _lib.check(rc, ctx.handle, "pa_stage_windows")
+
+
 def square_crop_single(image, norm_box, output_size=128, padding=0):
     """`YoloCrop.square_crop` contract on one host image: (True, uint8 HWC crop) / (False, None)."""
     image = np.ascontiguousarray(image)

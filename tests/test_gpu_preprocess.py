@@ -180,3 +180,63 @@ def test_full_size_batch_properties(torch_cuda):
         f = frames[fid[i]].cpu().numpy()
         ok, crop = resample.square_crop(f, tuple(boxes.reshape(-1, 4)[i]), 128, 30)
         assert ok and np.array_equal(a_np[i], crop), i
+
+
+def test_window_staging_matches_device_frames(torch_cuda, golden_dir, golden_frames):
+    """pa_stage_windows: crops cut from a staging buffer that holds only the window bytes (pulled from
+    pinned host frames, rest of the buffer poisoned) are the bytes cut from fully resident frames."""
+    torch = torch_cuda
+    from playaid_core_b200 import _lib
+    from playaid_core_b200.preprocess import crop_records, preprocess_crops, stage_windows
+
+    g = np.load(os.path.join(golden_dir, "crops.npz"))
+    frames_np = np.ascontiguousarray(np.stack(golden_frames))
+    H, W = frames_np.shape[1:3]
+    host = torch.from_numpy(frames_np).pin_memory()
+    dev_full = torch.from_numpy(frames_np).cuda()
+    for pad in (0, 30):
+        sel = np.nonzero(g["padding"] == pad)[0]
+        base = 5   # the match-wide record table carries global frame numbers
+        rec_global = crop_records(g["box"][sel], g["frame_id"][sel] + base, W, H)
+        rec_local = rec_global.copy(); rec_local[:, 0] -= base
+        rec_g, rec_l = torch.from_numpy(rec_global).cuda(), torch.from_numpy(rec_local).cuda()
+        staged = torch.full(tuple(host.shape), 0xAB, dtype=torch.uint8, device="cuda")
+        stage_windows(host, rec_g, staged, padding=pad, frame_base=base)
+        a, sa = preprocess_crops(staged, rec_l, 128, pad, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
+        b, sb = preprocess_crops(dev_full, rec_l, 128, pad, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
+        torch.cuda.synchronize()
+        assert torch.equal(sa, sb)
+        assert torch.equal(a, b), f"padding {pad}: {(a != b).flatten(1).any(1).sum().item()} crops differ"
+
+
+def test_match_stream_host_modes_agree(torch_cuda):
+    """MatchStream fed pinned host chunks (window staging on the copy stream, and in-place reads) labels
+    the clip exactly like the device-resident path."""
+    torch = torch_cuda
+    from playaid_core_b200.action_detector import ActionDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.fighter import boxes_from_records, yolo_pixels_batch
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from workloads import synthetic, weights
+
+    n, Hh, Ww = 96, 540, 960
+    recs = synthetic.synth_log_records(n, 2, seed=11)
+    boxes = boxes_from_records([r for f in recs for r in f]).reshape(n, 2, 4)
+    frames = synthetic.synth_frames(np.arange(n), yolo_pixels_batch(boxes, Ww, Hh), H=Hh, W=Ww, device="cuda", seed=5)
+    host = frames.cpu().pin_memory()
+    model = CNNActionDetector(ACTIONS, sequence_length=7, precision="f16", device="cuda").eval()
+    model.load_state_dict(weights.default_state_dict(0))
+    det = ActionDetector(model)
+    outs = {}
+    for mode in ("device", "stage", "inplace"):
+        det.host_mode = mode if mode != "device" else "stage"
+        st = det.stream(boxes, Hh, Ww)
+        src = frames if mode == "device" else host
+        for c in range(0, n, 32):
+            st.push(src[c : c + 32])
+        torch.cuda.synchronize()
+        outs[mode] = (st.label.clone(), st.logp.clone(), st.status.clone())
+    for mode in ("stage", "inplace"):
+        assert torch.equal(outs[mode][2], outs["device"][2])
+        assert torch.equal(outs[mode][0], outs["device"][0])
+        assert torch.equal(outs[mode][1], outs["device"][1]), mode
