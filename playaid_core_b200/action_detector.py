@@ -144,7 +144,7 @@ class ActionDetector:
         dev = self.model._device
         if self._stage_bufs is None or self._stage_bufs[0].shape[1:] != host_frames.shape[1:] or self._stage_bufs[0].shape[0] < host_frames.shape[0]:
             self._stage_bufs = [torch.empty(tuple(host_frames.shape), dtype=torch.uint8, device=dev) for _ in range(2)]
-            self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream = torch.cuda.Stream(dev, priority=-1)
             self._stage_ready = [torch.cuda.Event() for _ in range(2)]
             self._stage_free = [torch.cuda.Event() for _ in range(2)]
         slot = self._stage_i & 1

@@ -33,7 +33,7 @@ constexpr int C1_ROW_PITCH = 68;                              // floats per pixe
 constexpr int C1_ROWS_BYTES = 3 * 64 * C1_ROW_PITCH * 4;      // three conv rows, fp32
 
 template <int NA, int NB>
-__global__ void __launch_bounds__(C1_THREADS, 1) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
+__global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int NSTAGE = (NA == 1) ? 2 : 1;
@@ -203,6 +203,7 @@ static int launch_c1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cud
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PA_ERR_CUDA;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     int grid = a.n_crops;   // whole crops per CTA

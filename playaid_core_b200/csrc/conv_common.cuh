@@ -1,6 +1,7 @@
 // Shared by the tcgen05 convolution kernels (conv_gemm.cu, conv_patch.cu): tile constants and the
 // 16-warp TMEM epilogue.
 #pragma once
+#include <cstdlib>
 #include "pa_internal.cuh"
 #include "ptx.cuh"
 
@@ -8,7 +9,19 @@ namespace pa {
 
 constexpr int CG_FIRST_EPI_WARP = 2;
 constexpr int CG_EPI_WARPS = 16;
+// Register cap of the 18-warp conv CTAs. An SM sub-partition (16,384 registers) hosts 5 of those warps: at 88
+// registers they take 14,080 and leave room for one 64-register warp of the window-staging kernel, which must stay
+// resident beside them (at the natural 96 the conv CTA would have to wait for the staging kernel to drain).
+constexpr int CG_MAX_REGS = 88;
 constexpr int CG_THREADS = (CG_FIRST_EPI_WARP + CG_EPI_WARPS) * 32;  // TMA warp, MMA warp, 16 epilogue warps
+// Dynamic shared memory the conv kernels may plan with: 222 KB of the 228 KB per SM, so that a few 64-thread CTAs of
+// the window-staging kernel (1 KB of reserved shared memory each) can stay resident beside a conv CTA.
+inline size_t conv_smem_budget() {
+    static size_t v = 0;
+    if (!v) { const char* e = getenv("PA_CONV_SMEM_KB"); v = (size_t)(e ? atoi(e) : 222) * 1024; }
+    return v;
+}
+#define PA_CONV_SMEM_BUDGET conv_smem_budget()
 constexpr int CG_BLOCK_M = 128;
 constexpr int CG_BLOCK_K = 64;
 constexpr int CG_A_BYTES = CG_BLOCK_M * CG_BLOCK_K * 2;  // 16 KB

@@ -28,13 +28,13 @@ size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages) {
 }
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
     size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
-    int s = (int)((227 * 1024 - 1024 - 256) / stage);
+    int s = (int)((PA_CONV_SMEM_BUDGET - 1024 - 256) / stage);
     if (s > 8) s = 8;
     return s;
 }
 
 template <int BLOCK_N, int NA, int NB>
-__global__ void __launch_bounds__(CG_THREADS, 1)
+__global__ void __maxnreg__(CG_MAX_REGS)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

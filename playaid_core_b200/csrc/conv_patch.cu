@@ -20,7 +20,7 @@ struct PatchGeom {
 };
 
 template <int BLOCK_N, int NA, bool WRES>
-__global__ void __launch_bounds__(CG_THREADS, 1)
+__global__ void __maxnreg__(CG_MAX_REGS)
 conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, const PatchGeom pg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -163,7 +163,7 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
 int conv_patch_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out) {
     const int patch = (ht + 2) * wo * 128;
     const int b_bytes = block_n * CG_BLOCK_K * 2;
-    const size_t budget = 227 * 1024 - 1024 - 256;
+    const size_t budget = PA_CONV_SMEM_BUDGET - 1024 - 256;
     const size_t wres_bytes = (size_t)9 * kb * b_bytes;
     bool wres = wres_bytes <= 80 * 1024;
     for (int attempt = 0; attempt < 2; attempt++) {

@@ -18,6 +18,7 @@ struct pa_ctx {
     int device = 0;
     int num_sms = 148;
     int64_t launches = 0;
+    int* stage_sched = nullptr;   // pa_stage_windows scheduling scratch
     std::string last_error;
     decltype(&cuTensorMapEncodeTiled) encode_tiled = nullptr;
     int32_t* pp_status = nullptr;  // scratch per-crop status when the caller passes none
@@ -142,6 +143,7 @@ extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
     if (ctx && ctx->pp_status) cudaFree(ctx->pp_status);
     if (ctx && ctx->pp_deferred) cudaFree(ctx->pp_deferred);
     if (ctx && ctx->pp_plan) cudaFree(ctx->pp_plan);
+    if (ctx && ctx->stage_sched) cudaFree(ctx->stage_sched);
     delete ctx;
     return PA_OK;
 }
@@ -161,8 +163,10 @@ extern "C" int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_f
     p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
     p.n_frames = n_frames; p.H = H; p.W = W; p.pitch = pitch_bytes; p.fstride = frame_stride_bytes;
     p.boxes = boxes; p.n_crops = n_crops; p.padding = padding; p.frame_base = frame_base;
+    if (!ctx->stage_sched) PA_CUDA(ctx, cudaMalloc((void**)&ctx->stage_sched, PA_STAGE_SCHED_INTS * sizeof(int)));
+    p.sched = ctx->stage_sched;
     ProfSpan sp(ctx, "stage_windows", (cudaStream_t)stream);
-    if (launch_stage_windows(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "stage_windows launch");
+    if (launch_stage_windows(p, ctx->num_sms, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "stage_windows launch");
     ctx->launches += 1;
     return PA_OK;
 }

@@ -36,6 +36,23 @@ struct PPParams {
     int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);
+// numpy window image[cy-half-pad : cy+half+pad, cx-half-pad : cx+half+pad] of fighter.py:333-346, clipped as the
+// reference clips it (incl. numpy's negative-stop semantics for boxes entirely above / left of the frame)
+__host__ __device__ inline void crop_window(int cx, int cy, int sd, int H, int W, int padding, int& x0, int& y0, int& rw, int& rh) {
+    int half = sd / 2;
+    y0 = cy - half - padding; if (y0 < 0) y0 = 0;
+    int y1 = cy + half + padding; if (y1 > H) y1 = H;
+    x0 = cx - half - padding; if (x0 < 0) x0 = 0;
+    int x1 = cx + half + padding; if (x1 > W) x1 = W;
+    if (y1 < 0) { y1 += H; if (y1 < 0) y1 = 0; }  // numpy negative-stop semantics
+    if (x1 < 0) { x1 += W; if (x1 < 0) x1 = 0; }
+    if (y0 > H) y0 = H;
+    if (x0 > W) x0 = W;
+    rh = y1 - y0; rw = x1 - x0;
+    if (rh < 0) rh = 0;
+    if (rw < 0) rw = 0;
+}
+
 struct StageParams {
     const uint8_t* src;     // pinned host frames (device-visible)
     uint8_t* dst;           // device frame batch with the same pitch / frame stride
@@ -44,8 +61,11 @@ struct StageParams {
     int64_t pitch, fstride;
     const int32_t* boxes;   // crop records; record.frame - frame_base indexes the batch
     int n_crops, padding, frame_base;
+    int max_sm;             // workers only on SMs with %smid below this
+    int* sched;             // [PA_STAGE_SCHED_INTS] device scratch: work-item counter + workers per SM
 };
-int launch_stage_windows(const StageParams& p, cudaStream_t stream);
+constexpr int PA_STAGE_SCHED_INTS = 1 + 256;
+int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream);
 int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);
 size_t preprocess_geom_bytes();
 

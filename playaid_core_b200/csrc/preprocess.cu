@@ -115,23 +115,6 @@ __device__ __forceinline__ int sat_s16f(float v) {
     return iv < -32768 ? -32768 : (iv > 32767 ? 32767 : iv);
 }
 
-// numpy window image[cy-half-pad : cy+half+pad, cx-half-pad : cx+half+pad] of fighter.py:333-346, clipped as the
-// reference clips it (incl. numpy's negative-stop semantics for boxes entirely above / left of the frame)
-__device__ __forceinline__ void crop_window(int cx, int cy, int sd, int H, int W, int padding, int& x0, int& y0, int& rw, int& rh) {
-    int half = sd / 2;
-    y0 = cy - half - padding; if (y0 < 0) y0 = 0;
-    int y1 = cy + half + padding; if (y1 > H) y1 = H;
-    x0 = cx - half - padding; if (x0 < 0) x0 = 0;
-    int x1 = cx + half + padding; if (x1 > W) x1 = W;
-    if (y1 < 0) { y1 += H; if (y1 < 0) y1 = 0; }  // numpy negative-stop semantics
-    if (x1 < 0) { x1 += W; if (x1 < 0) x1 = 0; }
-    if (y0 > H) y0 = H;
-    if (x0 > W) x0 = W;
-    rh = y1 - y0; rw = x1 - x0;
-    if (rh < 0) rh = 0;
-    if (rw < 0) rw = 0;
-}
-
 __device__ void compute_geom(CropGeom& g, const int32_t* box, int H, int W, int n_frames, int out, int padding) {
     g.frame = box[0];
     int cx = box[1], cy = box[2], cw = box[3], ch = box[4];
@@ -1086,6 +1069,10 @@ int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
         if (e != cudaSuccess) return PA_ERR_CUDA;
+        // every kernel of the path asks for the maximum shared-memory carve-out: an SM never has to drain to
+        // re-partition L1/shared between kernels, so the staging kernel's CTAs can stay resident across them
+        cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(preprocess_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     preprocess_kernel<<<p.n_crops * PP_SPLIT, p.threads, p.smem_bytes, stream>>>(p);
@@ -1104,20 +1091,53 @@ size_t preprocess_geom_bytes() { return sizeof(CropGeom); }
 // exactly the 16-byte chunks preprocess_kernel reads (the clipped window rows of every crop) and writes them at
 // the same offsets of a device buffer with the frame batch's geometry, so a 1080p frame costs ~0.6 MB of bus
 // traffic instead of 6.2 MB and the copy of chunk i+1 can overlap the kernels of chunk i on another stream.
-constexpr int ST_SPLIT = 8;      // CTAs per crop
-constexpr int ST_THREADS = 256;
-constexpr int ST_UNROLL = 8;     // 16-byte loads in flight per thread
+// The kernel is a set of SMALL persistent workers (one warp, 8 x 16 B loads in flight per thread): a worker has
+// to sit beside the 2 x 256-thread preprocess CTAs or the 576-thread conv CTA that own an SM's registers while the
+// previous batch computes, and ~1 MB in flight GPU-wide covers PCIe latency. The block scheduler would pack many
+// such CTAs onto whichever SMs happen to be free at launch and starve the 1-CTA-per-SM conv kernels there, so each
+// CTA first registers on its SM (%smid) and exits if ST_PER_SM workers already live there; work items are handed
+// out through a global counter, so it does not matter which CTAs survive.
+constexpr int ST_SPLIT = 8;      // work items per crop
+constexpr int ST_THREADS = 32;     // one warp per worker: measured best beside the compute kernels (PA_ST_THREADS overrides)
+constexpr int ST_PER_SM = 1;
+constexpr int ST_CTAS_PER_SM = 4;  // launched; all but ST_PER_SM per SM retire at once
 
-__global__ void __launch_bounds__(ST_THREADS) stage_windows_kernel(const StageParams p) {
-    const int crop = blockIdx.x / ST_SPLIT, part = blockIdx.x - crop * ST_SPLIT;
+// streaming accesses that leave the SM's small L1 to the kernels computing beside this one
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream16(uint8_t* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int ST_UNROLL>   // 16-byte loads in flight per thread
+__global__ void __maxnreg__(64) stage_windows_kernel(const StageParams p) {
+  __shared__ int s_item;
+  if (threadIdx.x == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_item = ((int)smid < p.max_sm && atomicAdd(&p.sched[1 + (smid & 255)], 1) < ST_PER_SM) ? 0 : -1;
+  }
+  __syncthreads();
+  if (s_item < 0) return;
+  const int n_items = p.n_crops * ST_SPLIT;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(&p.sched[0], 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int crop = item / ST_SPLIT, part = item - crop * ST_SPLIT;
     const int32_t* box = p.boxes + (int64_t)crop * PA_BOX_STRIDE;
     const int frame = box[0] - p.frame_base;
     const int cw = box[3], ch = box[4];
     const int sd = cw > ch ? cw : ch;
-    if (frame < 0 || frame >= p.n_frames || sd < 0) return;
+    if (frame < 0 || frame >= p.n_frames || sd < 0) continue;
     int x0, y0, rw, rh;
     crop_window(box[1], box[2], sd, p.H, p.W, p.padding, x0, y0, rw, rh);
-    if (rw <= 0 || rh <= 0) return;
+    if (rw <= 0 || rh <= 0) continue;
     const int64_t fo = (int64_t)frame * p.fstride;
     const int64_t row0 = (int64_t)y0 * p.pitch + (int64_t)x0 * 3;
     const bool vec_ok = ((p.pitch & 15) == 0) && ((((uintptr_t)p.src + (uintptr_t)fo) & 15) == 0) &&
@@ -1129,39 +1149,57 @@ __global__ void __launch_bounds__(ST_THREADS) stage_windows_kernel(const StagePa
         const int total = rh * chunks;
         const int begin = (int)((int64_t)part * total / ST_SPLIT), end = (int)((int64_t)(part + 1) * total / ST_SPLIT);
         const int64_t base = fo + row0 - shift;
-        for (int i0 = begin + threadIdx.x; i0 < end; i0 += ST_THREADS * ST_UNROLL) {
+        for (int i0 = begin + threadIdx.x; i0 < end; i0 += blockDim.x * ST_UNROLL) {
             uint4 v[ST_UNROLL];
             int64_t off[ST_UNROLL];
 #pragma unroll
             for (int u = 0; u < ST_UNROLL; u++) {
-                const int i = i0 + u * ST_THREADS;
+                const int i = i0 + u * blockDim.x;
                 off[u] = -1;
                 if (i < end) {
                     const int r = chunks > 1 ? (int)__umulhi((uint32_t)i, ch_magic) : i;
                     const int c = i - r * chunks;
                     const int64_t o = base + (int64_t)r * p.pitch + (int64_t)c * 16;
-                    if (o + 16 <= p.frames_bytes) { off[u] = o; v[u] = __ldg((const uint4*)(p.src + o)); }
+                    if (o + 16 <= p.frames_bytes) { off[u] = o; v[u] = ld_stream16(p.src + o); }
                     else for (int k = 0; k < 16 && o + k < p.frames_bytes; k++) p.dst[o + k] = p.src[o + k];  // tail of the last row
                 }
             }
 #pragma unroll
             for (int u = 0; u < ST_UNROLL; u++)
-                if (off[u] >= 0) *(uint4*)(p.dst + off[u]) = v[u];
+                if (off[u] >= 0) st_stream16(p.dst + off[u], v[u]);
         }
     } else {
         const int rowb = rw * 3;
         const int total = rh * rowb;
         const int begin = (int)((int64_t)part * total / ST_SPLIT), end = (int)((int64_t)(part + 1) * total / ST_SPLIT);
-        for (int i = begin + threadIdx.x; i < end; i += ST_THREADS) {
+        for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
             const int r = i / rowb, c = i - r * rowb;
             const int64_t o = fo + row0 + (int64_t)r * p.pitch + c;
             p.dst[o] = p.src[o];
         }
     }
+  }
 }
 
-int launch_stage_windows(const StageParams& p, cudaStream_t stream) {
-    stage_windows_kernel<<<p.n_crops * ST_SPLIT, ST_THREADS, 0, stream>>>(p);
+int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream) {
+    int grid = p.n_crops * ST_SPLIT;
+    if (grid > ST_CTAS_PER_SM * num_sms) grid = ST_CTAS_PER_SM * num_sms;
+    if (cudaMemsetAsync(p.sched, 0, PA_STAGE_SCHED_INTS * sizeof(int), stream) != cudaSuccess) return PA_ERR_CUDA;
+    static int unroll = 0, threads = 0, max_sm = 0;
+    if (!unroll) {
+        const char* e;
+        unroll = (e = getenv("PA_ST_UNROLL")) ? atoi(e) : 8;
+        threads = (e = getenv("PA_ST_THREADS")) ? atoi(e) : ST_THREADS;
+        max_sm = (e = getenv("PA_ST_SMS")) ? atoi(e) : 1 << 20;
+        cudaFuncSetAttribute(stage_windows_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(stage_windows_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(stage_windows_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    StageParams q = p;
+    q.max_sm = max_sm;
+    if (unroll == 2) stage_windows_kernel<2><<<grid, threads, 0, stream>>>(q);
+    else if (unroll == 4) stage_windows_kernel<4><<<grid, threads, 0, stream>>>(q);
+    else stage_windows_kernel<8><<<grid, threads, 0, stream>>>(q);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
