@@ -329,7 +329,10 @@ def run_gpu(args):
     for hb, src in zip(host, resident):
         hb.copy_(src)
     stage = torch.empty((BATCH_FRAMES, H, W, 3), dtype=torch.uint8, device=dev)
-    out_host = torch.empty((BATCH_FRAMES * N_FIGHTERS, 2), dtype=torch.float32).pin_memory()
+    # results land in pinned host memory asynchronously (contiguous buffers, alternating by step: a strided host view
+    # would make torch stage the copy synchronously and stop the host from running ahead of the GPU)
+    lab_host = torch.empty((2, BATCH_FRAMES * N_FIGHTERS), dtype=torch.int32).pin_memory()
+    prob_host = torch.empty((2, BATCH_FRAMES * N_FIGHTERS), dtype=torch.float32).pin_memory()
     h2d = BATCH_FRAMES * H * W * 3
     d2h = BATCH_FRAMES * N_FIGHTERS * 8
 
@@ -342,8 +345,8 @@ def run_gpu(args):
             st, a, b = step(host[i % 2])
         if b > a:
             n = (b - a) * N_FIGHTERS
-            out_host[:n, 0].copy_(st.label[a:b].reshape(-1).float(), non_blocking=True)
-            out_host[:n, 1].copy_(st.prob[a:b].reshape(-1), non_blocking=True)
+            lab_host[i & 1, :n].copy_(st.label[a:b].reshape(-1), non_blocking=True)
+            prob_host[i & 1, :n].copy_(st.prob[a:b].reshape(-1), non_blocking=True)
 
     Ke = max(4, min(K, 20))
     e2e_runs = {}

@@ -12,7 +12,7 @@ from workloads import synthetic, weights
 
 H, W, B, F = 1080, 1920, 256, 2
 dev = torch.device("cuda", 0)
-recs = synthetic.synth_log_records(B * 16, F, seed=2024)
+recs = synthetic.synth_log_records(10800, F, seed=2024)[: B * 16]
 boxes = boxes_from_records([r for f in recs for r in f]).reshape(B * 16, F, 4)
 px = yolo_pixels_batch(boxes, W, H)
 frames = synthetic.synth_frames(np.arange(B), px[:B], device=dev, seed=1)
@@ -26,7 +26,15 @@ torch.cuda.synchronize()
 e0.record()
 for i in range(5): stage_windows(host[i % 2], rec, buf, 30, 0)
 e1.record(); torch.cuda.synchronize()
-print("stage alone ms/chunk", e0.elapsed_time(e1) / 5)
+def wbytes(p4, pad=30):
+    cx, cy, cw, ch = [p4[..., i].astype(np.int64) for i in range(4)]
+    half = np.maximum(cw, ch) // 2
+    y0 = np.maximum(cy - half - pad, 0); y1 = np.minimum(cy + half + pad, H)
+    x0 = np.maximum(cx - half - pad, 0); x1 = np.minimum(cx + half + pad, W)
+    return int((3 * np.maximum(y1 - y0, 0) * np.maximum(x1 - x0, 0)).sum())
+ms = e0.elapsed_time(e1) / 5
+print("stage alone ms/chunk", ms, "window MB", wbytes(px[:B]) / 1e6, "GB/s", wbytes(px[:B]) / ms / 1e6)
+print("mean window MB/chunk over chunks 0..7", wbytes(px[: 8 * B]) / 8e6)
 e0.record()
 for i in range(3): buf.copy_(host[i % 2], non_blocking=True)
 e1.record(); torch.cuda.synchronize()
