@@ -70,6 +70,12 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
                 }
             }
         };
+        if (args.debug & 1) {   // experiment: how fast is the kernel without an epilogue?
+            mbar_wait(&tfull[acc], acc_ph);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            continue;
+        }
         load_res(wq * 16, rh0, rh1, rl0, rl1);
         mbar_wait(&tfull[acc], acc_ph);
         tc_fence_after();

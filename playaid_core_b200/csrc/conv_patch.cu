@@ -79,7 +79,9 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = stages + (size_t)st * stage_bytes;
-                        if (elect_one()) {
+                        if ((args.debug & 2) && dxi > 0) {   // experiment: skip two of the three patch loads
+                            if (elect_one()) mbar_arrive(&full[st]);
+                        } else if (elect_one()) {
                             mbar_arrive_expect_tx(&full[st], stage_bytes);
 #pragma unroll
                             for (int pl = 0; pl < NA; pl++)
@@ -195,8 +197,12 @@ static int launch_p(const ConvMaps& maps, const ConvArgs& args, const PatchGeom&
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
-int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
+int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args_in, int block_n, int n_a, int ht, bool wres, size_t smem,
                       int num_sms, cudaStream_t stream) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PA_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    ConvArgs args = args_in;
+    args.debug = dbg;
     PatchGeom pg;
     pg.patch_bytes = (ht + 2) * args.wo * 128;
     pg.row_bytes = args.wo * 128;

@@ -95,6 +95,7 @@ struct ConvArgs {
     bf16* out_lo;         // lo plane (split precision) or nullptr
     float* out_f32;       // fp32 output [M][cout] or nullptr
     int f16;              // 16-bit operand format: 0 bf16, 1 IEEE half
+    int debug;            // PA_CONV_DEBUG experiments (results are wrong): 1 = epilogue only drains barriers, 2 = one TMA patch per tile
 };
 
 int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms,

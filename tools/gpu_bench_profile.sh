@@ -1,10 +1,21 @@
 #!/bin/bash
-# bench + ncu evidence on the GPU box. Usage: bash tools/gpu_bench_profile.sh <tag> [ncu-kernel-regex] [skip count]
+# bench + ncu evidence on the GPU box (one ncu invocation per call).
+#   bash tools/gpu_bench_profile.sh <tag> bench                       benches (all precisions + reference arm) + ncu launch list
+#   bash tools/gpu_bench_profile.sh <tag> full [regex] [skip] [count] one `ncu --set full` capture of the top kernels
 TAG=${1:-r01}
-KREGEX=${2:-"conv_gemm|conv1_kernel|preprocess"}
-SKIP=${3:-30}
-COUNT=${4:-14}
+MODE=${2:-bench}
+KREGEX=${3:-"conv_gemm|conv_patch|conv1_kernel|preprocess_kernel"}
+SKIP=${4:-30}
+COUNT=${5:-14}
 mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
+if [ "$MODE" = "full" ]; then
+  $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s $SKIP -c $COUNT \
+      -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+  echo "ncu full exit $?"
+  exit 0
+fi
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 echo "bench exit $?"; tail -n 5 gpurun_out/bench_$TAG.err
 python bench.py --steps 10 --warmup 3 --precision f16x2 --no-cpu-baseline > gpurun_out/bench_${TAG}_f16x2.json 2> gpurun_out/bench_${TAG}_f16x2.err
@@ -24,12 +35,7 @@ for n in ["bench_$TAG","bench_${TAG}_f16x2","bench_${TAG}_bf16","bench_${TAG}_re
         for k,v in sorted(ks.items(), key=lambda kv:-kv[1]["ms_per_step"])[:8]: print("   %-40s %.3f ms %.1f%%"%(k,v["ms_per_step"],100*v["share"]))
     except Exception as e: print(n, "ERR", e)
 PY
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'preprocess|conv|maxpool|avgpool|head|split' -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'preprocess|conv|maxpool|avgpool|head|split|stage' -c 400 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
-$CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s $SKIP -c $COUNT \
-    -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
-echo "ncu full exit $?"

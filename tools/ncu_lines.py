@@ -2,7 +2,9 @@
 """Per-source-line instruction / stall-sample shares from an .ncu-rep (needs -lineinfo + --import-source on).
    python tools/ncu_lines.py rep.ncu-rep [top_n]"""
 import csv, io, subprocess, sys, collections
+import os
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+only = os.environ.get("NCU_FILE")   # restrict to one source file, e.g. NCU_FILE=preprocess.cu
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = None; acc = collections.OrderedDict(); fname = ""
@@ -10,6 +12,7 @@ for r in rows:
     if len(r) >= 2 and r[0] == "File Path": fname = r[1].split("/")[-1]; continue
     if len(r) > 8 and r[0] == "Line No": hdr = r; ii = hdr.index("Instructions Executed"); sm = hdr.index("# Samples"); continue
     if hdr and len(r) == len(hdr) and r[0].strip():
+        if only and fname != only: continue
         key = (fname, r[0], r[1].strip())
         a = acc.setdefault(key, [0.0, 0.0, 0])
         def num(x):
