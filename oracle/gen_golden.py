@@ -11,6 +11,7 @@ rebuild without the reference:
                 + the fighter_test.py record (Appendix D1)
   windows.npz   action_sample_from_frame_middle_out (dataset_utils.py:109-138)
   timeline.json load_ground_truth_from_path (timeline.py:204-280) on tests/golden/sample_log.jsonl
+  ai_timeline.json load_timeline_from_ai_output (timeline.py:52-105) on golden_ai_output(): digest + samples
   model.npz     CNNActionDetector(seed 0, default init).forward on a seeded input
                 (models/cnn_action_detector.py:86-92) and the argmax / exp head (ai_runner.py:474-477)
 """
@@ -65,6 +66,46 @@ def golden_boxes():
     for _ in range(8):
         cases.append((2, (rng.uniform(0.3, 0.7), rng.uniform(0.3, 0.7), rng.uniform(0.4, 0.9), rng.uniform(0.4, 0.9)), 30))
     return cases
+
+
+def golden_ai_output(n_frames: int = 600, fighters=("Joker", "Pikachu")) -> dict:
+    """Deterministic ai_output.yaml content (the schema AIRunner.write_output dumps, ai_runner.py:493-520)."""
+    rng = np.random.default_rng(17)
+    acts = ["Jab", "Wait", "Run", "Shield", "ForwardAir", "Damaged"]
+    out = {}
+    for name in fighters:
+        per = {}
+        for i in range(n_frames):
+            cx, cy, w, h = rng.uniform(0.1, 0.9), rng.uniform(0.2, 0.8), rng.uniform(0.05, 0.3), rng.uniform(0.08, 0.4)
+            per[i] = {"crop": f"0 {cx:.6f} {cy:.6f} {w:.6f} {h:.6f} 0", "action": acts[int(rng.integers(len(acts)))],
+                      "predicted_action_confidence": float(np.round(rng.uniform(5, 100), 4))}
+            if i % 7 == 0:
+                per[i]["damage"] = float(np.round(rng.uniform(0, 150), 2))
+        out[name] = per
+    return out
+
+
+def gen_ai_timeline():
+    """load_timeline_from_ai_output (timeline.py:52-105) on golden_ai_output(): digest + sampled frames."""
+    import hashlib
+    import tempfile
+
+    import yaml
+
+    from oracle import ref_shims
+
+    ref_shims.install()
+    from playaid.timeline import load_timeline_from_ai_output
+
+    path = os.path.join(tempfile.mkdtemp(), "ai_output.yaml")
+    with open(path, "w") as f:
+        yaml.dump(golden_ai_output(), f)
+    tl = load_timeline_from_ai_output(path)
+    blob = json.dumps(tl, sort_keys=True).encode()
+    with open(os.path.join(GOLD, "ai_timeline.json"), "w") as f:
+        json.dump({"n_frames": len(tl), "sha256": hashlib.sha256(blob).hexdigest(),
+                   "samples": {str(i): tl[i] for i in (0, 1, 7, 299, 599)}}, f)
+    print("ai timeline frames:", len(tl))
 
 
 def main():
@@ -161,4 +202,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ai_timeline":   # regenerate only that fixture
+        gen_ai_timeline()
+    else:
+        main()
+        gen_ai_timeline()

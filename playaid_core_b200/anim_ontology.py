@@ -7,6 +7,9 @@
   `STAGE_ENUM_TO_DATA` (reference playaid/anim_ontology.py:497-570) that
   `Fighter.set_from_json` uses for the bbox projection (playaid/fighter.py:479-491).
   Unknown stage ids fall back to stage 0 there, and here.
+* `FIGHTER_NAME_TO_ENUM` -- fighter display name -> the game's fighter-kind id, for the fighters the path's
+  defaults, fixtures and synthetic logs name (a slice of reference playaid/anim_ontology.py:395-495;
+  callers with other fighters pass their own mapping to `load_timeline_from_ai_output`).
 """
 
 ACTIONS = [
@@ -30,3 +33,5 @@ STAGE_FOV = {
 
 def stage_fov(stage_id: int) -> int:
     return STAGE_FOV.get(stage_id, STAGE_FOV[0])
+
+FIGHTER_NAME_TO_ENUM = {"Mario": 0, "Pikachu": 8, "Diddy Kong": 39, "Joker": 82, "Byleth": 86}

@@ -176,4 +176,81 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
     }
 }
 
+// Fast path for the Cout = 64 layers (layer1): one 16-column chunk per warp for the whole kernel, so scale/shift
+// live in registers, the residual is requested before the accumulator is waited for, and the TMEM buffer is
+// handed back to the MMA warp as soon as it has been read (the stores overlap the next tile's MMAs).
+template <bool F16, bool SPLIT>
+__device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                             int warp, int lane, int total_tiles) {
+    const int q = warp & 3;
+    const int c0 = ((warp - CG_FIRST_EPI_WARP) >> 2) * 16;
+    const int r = q * 32 + lane;
+    float sc[16], sh[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 a = __ldg((const float4*)(args.scale + c0) + i), b = __ldg((const float4*)(args.shift + c0) + i);
+        sc[4 * i] = a.x; sc[4 * i + 1] = a.y; sc[4 * i + 2] = a.z; sc[4 * i + 3] = a.w;
+        sh[4 * i] = b.x; sh[4 * i + 1] = b.y; sh[4 * i + 2] = b.z; sh[4 * i + 3] = b.w;
+    }
+    const bool has_res = args.res_hi != nullptr;
+    const bool has_res_lo = args.res_lo != nullptr;
+    const bool relu = args.relu != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        const int64_t o = ((int64_t)tile * CG_BLOCK_M + r) * 64 + c0;
+        uint4 rh0 = make_uint4(0, 0, 0, 0), rh1 = rh0, rl0 = rh0, rl1 = rh0;
+        if (has_res) {
+            const uint4* rp = (const uint4*)(args.res_hi + o);
+            rh0 = __ldg(rp); rh1 = __ldg(rp + 1);
+            if (has_res_lo) { const uint4* lp = (const uint4*)(args.res_lo + o); rl0 = __ldg(lp); rl1 = __ldg(lp + 1); }
+        }
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc[i], sh[i]);
+        if (has_res) {
+            const uint32_t w[8] = {rh0.x, rh0.y, rh0.z, rh0.w, rh1.x, rh1.y, rh1.z, rh1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) { v[2 * i] += dec16<F16>((uint16_t)(w[i] & 0xFFFF)); v[2 * i + 1] += dec16<F16>((uint16_t)(w[i] >> 16)); }
+            if (has_res_lo) {
+                const uint32_t x[8] = {rl0.x, rl0.y, rl0.z, rl0.w, rl1.x, rl1.y, rl1.z, rl1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) { v[2 * i] += dec16<F16>((uint16_t)(x[i] & 0xFFFF)); v[2 * i + 1] += dec16<F16>((uint16_t)(x[i] >> 16)); }
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint32_t h[8], l[8];
+        if (SPLIT) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) split2<F16>(v[2 * i], v[2 * i + 1], h[i], l[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
+        }
+        uint4* op = (uint4*)(args.out_hi + o);
+        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        if (SPLIT) {
+            uint4* lp = (uint4*)(args.out_lo + o);
+            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+        }
+    }
+}
+
+// true when epilogue_n64 applies
+__device__ __forceinline__ bool epilogue_n64_ok(const ConvArgs& a) {
+    return a.n_tiles == 1 && a.cout == 64 && a.scale && a.shift && a.out_hi && !a.out_f32 && (a.m_total % CG_BLOCK_M) == 0 && !a.debug;
+}
+
 }  // namespace pa

@@ -148,7 +148,15 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
     } else {
         // ===================== epilogue (warps 2..17) =====================
         const bool split_out = args.out_lo != nullptr;
-        if (args.f16) {
+        if (BLOCK_N == 64 && epilogue_n64_ok(args)) {
+            if (args.f16) {
+                if (split_out) epilogue_n64<true, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+                else epilogue_n64<true, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+            } else {
+                if (split_out) epilogue_n64<false, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+                else epilogue_n64<false, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
+            }
+        } else if (args.f16) {
             if (split_out) epilogue<BLOCK_N, true, true>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
             else epilogue<BLOCK_N, true, false>(args, tfull, tempty, tmem_base, warp, lane, total_tiles);
         } else {

@@ -168,3 +168,46 @@ def test_four_fighters_cfg3(setup):
     r = det.classify_clip(frames, boxes)
     assert (r["label"].cpu().numpy() == label).all()
     assert _rel(r["logp"].cpu().numpy(), logp).max() < PARITY_TOL
+
+
+def test_ai_runner_facade(tmp_path):
+    """AIRunner surface (reference ai_runner.py:426-520, 592-608): 1-indexed frames, batched
+    run_action_recognition == per-window action_recognition, yaml round trip into the timeline loader."""
+    import torch
+    import yaml
+
+    from playaid_core_b200.ai_runner import AIRunner
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.fighter import boxes_from_records, yolo_pixels_batch
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from playaid_core_b200.timeline import load_timeline_from_ai_output
+    from workloads import synthetic, weights
+
+    n, Hh, Ww = 48, 540, 960
+    recs = synthetic.synth_log_records(n, 2, seed=21)
+    boxes = boxes_from_records([r for f in recs for r in f]).reshape(n, 2, 4)
+    frames = synthetic.synth_frames(np.arange(n), yolo_pixels_batch(boxes, Ww, Hh), H=Hh, W=Ww, device="cuda", seed=9)
+    model = CNNActionDetector(ACTIONS, sequence_length=7, precision="f16", device="cuda").eval()
+    model.load_state_dict(weights.calibrated_state_dict(0))
+    out_file = str(tmp_path / "ai_output.yaml")
+    names = ["Byleth", "Diddy Kong"]
+    runner = AIRunner(frames, boxes, names, model, ai_output_file=out_file, chunk=16)
+    assert runner.max_frames == n
+    data = runner.run_action_recognition()
+    assert sorted(data["Byleth"].keys()) == list(range(n - 1))      # frame numbers 1..n-1 -> indices 0..n-2
+    for frame_num, fighter in ((1, "Byleth"), (5, "Diddy Kong"), (30, "Byleth"), (n - 1, "Diddy Kong")):
+        x, cid, pid, info = runner.action_recognition(frame_num, fighter)
+        assert tuple(x.shape) == (1, 7, 3, 128, 128) and x.dtype == torch.float32 and float(x.max()) <= 1.0
+        assert cid == names.index(fighter) and len(info["frames"]) == 7 and info["frames"][0].shape == (128, 128, 3)
+        e = data[fighter][frame_num - 1]
+        assert e["action"] == info["predicted_action"] == ACTIONS[int(pid)]
+        assert abs(e["predicted_action_confidence"] - info["confidence"]) < 1e-3 * max(1.0, info["confidence"])
+        assert e["crop"] == str(info["crop"])
+    runner.write_output()
+    ok, loaded = AIRunner(frames, boxes, names, model, ai_output_file=out_file).load_ai_output()
+    assert ok and loaded["Diddy Kong"][3]["action"] == data["Diddy Kong"][3]["action"]
+    # a second run is a no-op unless overwrite (ai_runner.py:503-505)
+    again = AIRunner(frames, boxes, names, model, ai_output_file=out_file)
+    assert again.run_action_recognition() == yaml.safe_load(open(out_file))
+    tl = load_timeline_from_ai_output(out_file, max_frames=n - 1, fighters=names)
+    assert len(tl) == n - 1 and tl[4][1]["action"] == data["Diddy Kong"][4]["action"] and tl[4][1]["fighter_name"] == 39

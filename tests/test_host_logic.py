@@ -86,3 +86,38 @@ def test_synthetic_frames_deterministic():
     a = synthetic.synth_frames([5], b, device="cpu")
     c = synthetic.synth_frames([5], b, device="cpu")
     assert a.shape == (1, 1080, 1920, 3) and bool((a == c).all())
+
+
+def test_load_timeline_from_ai_output_matches_reference(golden_dir, tmp_path):
+    """ai_output.yaml -> timeline records, pinned by the reference's own loader
+    (oracle/gen_golden.py::gen_ai_timeline); kwargs lift the hard-coded 600 frames / fighter pair."""
+    import hashlib
+    import json
+    import os
+
+    import yaml
+
+    from oracle.gen_golden import golden_ai_output
+    from playaid_core_b200.timeline import load_timeline_from_ai_output
+
+    gold = json.load(open(os.path.join(golden_dir, "ai_timeline.json")))
+    path = str(tmp_path / "ai_output.yaml")
+    with open(path, "w") as f:
+        yaml.dump(golden_ai_output(), f)
+    tl = load_timeline_from_ai_output(path)
+    assert len(tl) == gold["n_frames"] == 600
+    for i, frame in gold["samples"].items():
+        assert tl[int(i)] == frame
+    assert hashlib.sha256(json.dumps(tl, sort_keys=True).encode()).hexdigest() == gold["sha256"]
+    # kwargs: another pair, every frame in the file
+    small = {"Byleth": {i: {"crop": "0 0.5 0.5 0.1 0.2 0", "action": "Wait"} for i in range(5)},
+             "Diddy Kong": {i: {"crop": "0 0.4 0.5 0.1 0.2 0", "action": "Run"} for i in range(5)}}
+    with open(path, "w") as f:
+        yaml.dump(small, f)
+    tl = load_timeline_from_ai_output(path, max_frames=None, fighters=["Byleth", "Diddy Kong"])
+    assert len(tl) == 5 and [r["fighter_id"] for r in tl[0]] == [0, 1]
+    assert tl[2][1]["fighter_name"] == 39 and tl[2][1]["action"] == "Run" and tl[2][0]["stage_id"] == 86
+    # the AI crop string overrides the projected box (fighter.py:503-504)
+    from playaid_core_b200.fighter import boxes_from_timeline
+    b = boxes_from_timeline(tl)
+    assert b.shape == (5, 2, 4) and abs(b[0, 1, 0] - 0.4) < 1e-12 and abs(b[0, 0, 3] - 0.2) < 1e-12
