@@ -349,13 +349,15 @@ def run_gpu(args):
             prob_host[i & 1, :n].copy_(st.prob[a:b].reshape(-1), non_blocking=True)
 
     Ke = max(4, min(K, 20))
-    e2e_runs = {}
+    e2e_runs, e2e_bytes = {}, {}
     for mode in ("whole", "inplace", "windows"):
         for i in range(2):
             e2e_step(i, mode)
         barrier()
+        chunks_used = []
         e0.record()
         for i in range(Ke):
+            chunks_used.append(state["chunk"] % n_chunks)
             e2e_step(i, mode)
         e1.record()
         barrier()
@@ -363,10 +365,11 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_runs[mode] = world * Ke * BATCH_FRAMES / (float(t.item()) / 1e3)
-    wb_e2e = float(window_bytes(px[: n_chunks * BATCH_FRAMES]).sum() / n_chunks)  # mean window bytes of a 256-frame step
+        # window bytes of exactly the chunks this loop crossed PCIe with (they vary along the match)
+        e2e_bytes[mode] = float(np.mean([window_bytes(px[c * BATCH_FRAMES : (c + 1) * BATCH_FRAMES]).sum() for c in chunks_used]))
     e2e_mode = max(e2e_runs, key=e2e_runs.get)
     e2e_value = e2e_runs[e2e_mode]
-    h2d = BATCH_FRAMES * H * W * 3 if e2e_mode == "whole" else int(wb_e2e)
+    h2d = BATCH_FRAMES * H * W * 3 if e2e_mode == "whole" else int(e2e_bytes[e2e_mode])
     e2e_desc = {"whole": "whole frames copied to HBM with cudaMemcpyAsync, then the device path",
                 "inplace": "pinned host frames read in place by the preprocess kernel (window bytes only)",
                 "windows": "pa_stage_windows pulls the crop windows from pinned host frames on a copy stream (window bytes only), "
@@ -431,7 +434,8 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "mode": e2e_desc, "whole_frames_memcpy": e2e_runs["whole"], "in_place_pinned": e2e_runs["inplace"],
-                    "window_staging": e2e_runs["windows"]},
+                    "window_staging": e2e_runs["windows"],
+                    "pcie_gb_per_s": h2d * e2e_value / world / BATCH_FRAMES / 1e9},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_preprocess": roofline_pre, "kernels": kernels,
             "cpu_baseline": cpu,

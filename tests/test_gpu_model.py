@@ -211,3 +211,30 @@ def test_ai_runner_facade(tmp_path):
     assert again.run_action_recognition() == yaml.safe_load(open(out_file))
     tl = load_timeline_from_ai_output(out_file, max_frames=n - 1, fighters=names)
     assert len(tl) == n - 1 and tl[4][1]["action"] == data["Diddy Kong"][4]["action"] and tl[4][1]["fighter_name"] == 39
+
+
+def test_chunking_and_frame_sharding_are_invisible(setup):
+    """Size-independent properties of the streaming path: labels / log-probs do not depend on how the clip is
+    chunked, nor on cutting it into per-rank frame shards with a 27-frame halo -- bit for bit."""
+    torch, sd, _ = setup
+    from playaid_core_b200.action_detector import ActionDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from playaid_core_b200.parallel import frame_shard
+
+    N = 150
+    frames, boxes = _clip(N, seed=77)
+    det = ActionDetector(CNNActionDetector(ACTIONS, sequence_length=7, precision="f16").eval().load_state_dict(sd))
+    whole = det.classify_clip(frames, boxes, chunk=256)
+    small = det.classify_clip(frames, boxes, chunk=37)
+    assert torch.equal(whole["label"], small["label"]) and torch.equal(whole["logp"], small["logp"])
+    for world in (2, 3):
+        labels, logps = [], []
+        for rank in range(world):
+            lo, hi, hlo, hhi = frame_shard(N, rank, world)
+            r = det.classify_shard(frames[hlo:hhi], boxes[hlo:hhi], hlo, (lo, hi), N, chunk=64)
+            assert r["label"].shape[0] == hi - lo
+            labels.append(r["label"]); logps.append(r["logp"])
+        assert torch.equal(torch.cat(labels), whole["label"]), world
+        assert torch.equal(torch.cat(logps), whole["logp"]), world
+    assert len(set(whole["label"].flatten().tolist())) >= 5   # the calibrated net spreads its predictions
