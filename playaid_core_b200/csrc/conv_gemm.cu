@@ -95,7 +95,9 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
                         uint8_t* sb = sa + NA * CG_A_BYTES;
-                        if (elect_one()) {
+                        if (args.debug & 2) {   // experiment: no operand loads at all (pure MMA issue rate)
+                            if (elect_one()) mbar_arrive(&full[st]);
+                        } else if (elect_one()) {
                             mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
 #pragma unroll
                             for (int pl = 0; pl < NA; pl++)
@@ -186,7 +188,11 @@ static int launch_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cud
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
-int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms, cudaStream_t stream) {
+int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args_in, int block_n, int n_a, int n_b, int num_sms, cudaStream_t stream) {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PA_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    ConvArgs args = args_in;
+    args.debug = dbg;
 #define PA_CG_CASE(BN, A, B) \
     if (block_n == BN && n_a == A && n_b == B) return launch_t<BN, A, B>(maps, args, num_sms, stream);
     PA_CG_CASE(64, 1, 1) PA_CG_CASE(128, 1, 1) PA_CG_CASE(256, 1, 1)

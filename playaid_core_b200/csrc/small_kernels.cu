@@ -168,16 +168,21 @@ int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
-// ---------------------------------------------------------------- temporal head, one CTA (128 threads) per window
+// ---------------------------------------------------------------- temporal head, one CTA (512 threads) per window
 // proj[f][t*512 + o] = sum_i W1d[o][i][t] * feat[f][i]; the Conv1d over a window is the sum over its
 // 7 slots of the matching projection rows (+ bias), so no window tensor is ever built.
-__global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
+// The MLP rows are split four ways over the 512 threads (partial sums combined through shared memory) and the
+// loops are unrolled 16-fold: the weights come from L2, and a single 512-long dependent chain per thread left the
+// kernel waiting on one load at a time.
+__global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
     __shared__ float h[512];
+    __shared__ float part[4][128];
     __shared__ float y1[128];
     __shared__ float y2[128];
     const int w = blockIdx.x, t = threadIdx.x;
     const int pitch = a.seq * 512;
-    for (int o = t; o < 512; o += 128) {
+    {
+        const int o = t;
         float s = a.b1d[o];
         for (int k = 0; k < a.seq; k++) {
             int f = a.win_idx[(int64_t)w * a.seq + k];
@@ -188,14 +193,21 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
     }
     __syncthreads();
     {
-        float s = a.b1[t];
-        for (int i = 0; i < 512; i++) s = fmaf(a.w1t[i * 128 + t], h[i], s);
-        y1[t] = fmaxf(s, 0.f);
+        const int j = t & 127, p = t >> 7;
+        const float* wp = a.w1t + (size_t)(p * 128) * 128 + j;
+        const float* hp = h + p * 128;
+        float s = 0.f;
+#pragma unroll 16
+        for (int i = 0; i < 128; i++) s = fmaf(__ldg(wp + i * 128), hp[i], s);
+        part[p][j] = s;
     }
+    __syncthreads();
+    if (t < 128) y1[t] = fmaxf(a.b1[t] + ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])), 0.f);
     __syncthreads();
     if (t < a.n_actions) {
         float s = a.b2[t];
-        for (int i = 0; i < 128; i++) s = fmaf(a.w2t[i * a.n_actions + t], y1[i], s);
+#pragma unroll 16
+        for (int i = 0; i < 128; i++) s = fmaf(__ldg(a.w2t + i * a.n_actions + t), y1[i], s);
         y2[t] = s;
     }
     __syncthreads();
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(128) head_kernel(const HeadArgs a) {
 
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
     if (a.n_actions > 128 || a.n_win <= 0) return PA_ERR_INVALID_ARG;
-    head_kernel<<<a.n_win, 128, 0, stream>>>(a);
+    head_kernel<<<a.n_win, 512, 0, stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
