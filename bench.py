@@ -413,15 +413,23 @@ def run_gpu(args):
         cls_flops = crops_per_step * FLOP_PER_CROP
         tensor_achieved = cls_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
         hbm_achieved = pre_bytes / (pre_ms / 1e3) / 1e9 if pre_ms > 0 else 0.0
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram__bytes_read+write per step, from the ncu capture of this command
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath))
+            except Exception:
+                traffic = {}
         roofline = {
             "bound": "tensor", "kernel": "conv_gemm_kernel + conv1_kernel (ResNet-18 implicit GEMMs, all layers)",
             "achieved": tensor_achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": tensor_achieved / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+            "frac": tensor_achieved / pk["bf16_tflops_sustained"], "traffic": (traffic.get("conv") or {}).get("dram_bytes"),
+            "traffic_source": traffic.get("source"), "peak_source": pk["source"] + " (sustained)",
             "algorithmic_flop_per_step": cls_flops, "ms_per_step": conv_ms, "share_of_step": conv_ms / (total_ms / Kp),
         }
         roofline_pre = {
             "bound": "hbm", "kernel": "preprocess_kernel", "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": hbm_achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+            "frac": hbm_achieved / pk["hbm_gbs"], "traffic": (traffic.get("preprocess") or {}).get("dram_bytes"), "peak_source": pk["source"],
             "algorithmic_bytes_per_step": pre_bytes, "ms_per_step": pre_ms, "share_of_step": pre_ms / (total_ms / Kp),
         }
 

@@ -147,6 +147,11 @@ class ActionDetector:
             self._copy_stream = torch.cuda.Stream(dev, priority=-1)
             self._stage_ready = [torch.cuda.Event() for _ in range(2)]
             self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            # the buffers may be recycled blocks of the caching allocator: order the copy stream after whatever the
+            # allocating stream still has queued on them
+            alloc_done = torch.cuda.Event()
+            alloc_done.record(torch.cuda.current_stream(dev))
+            self._copy_stream.wait_event(alloc_done)
         slot = self._stage_i & 1
         self._stage_i += 1
         buf = self._stage_bufs[slot][: host_frames.shape[0]]

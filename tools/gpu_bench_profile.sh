@@ -36,6 +36,6 @@ for n in ["bench_$TAG","bench_${TAG}_f16x2","bench_${TAG}_bf16","bench_${TAG}_re
     except Exception as e: print(n, "ERR", e)
 PY
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'preprocess|conv|maxpool|avgpool|head|split|stage' -c 400 --csv \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:'preprocess|conv|maxpool|avgpool|head|split|stage' -c 400 --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "ncu launches exit $?"
