@@ -107,6 +107,18 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def poll_once(self):
+        """One sample from the calling thread (the timed loop calls this between enqueues: the GPU is busy with
+        the queued steps, and the sample does not depend on the polling thread winning the GIL)."""
+        if self.nvml is None or self.handle is None:
+            return
+        nv = self.nvml
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            self.samples.append((nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM), int(reasons(self.handle))))
+        except Exception:
+            pass
+
     def start(self):
         if self.nvml is not None:
             self.running = True
@@ -322,6 +334,8 @@ def run_gpu(args):
     e0.record()
     for i in range(K):
         step(resident[(Wm + i) % N_RESIDENT], slot=i)
+        if rank == 0 and i >= 2 and (i % 4 == 2 or i == K - 1):
+            sampler.poll_once()   # the host runs ahead of the GPU: this lands while earlier steps execute
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), lab_local)
     e1.record()
