@@ -334,7 +334,7 @@ def run_gpu(args):
     e0.record()
     for i in range(K):
         step(resident[(Wm + i) % N_RESIDENT], slot=i)
-        if rank == 0 and i >= 2 and (i % 4 == 2 or i == K - 1):
+        if rank == 0 and (i % 4 == 2 or i == K - 1):
             sampler.poll_once()   # the host runs ahead of the GPU: this lands while earlier steps execute
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), lab_local)
