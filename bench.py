@@ -267,7 +267,11 @@ def run_gpu(args):
     if world > 1:
         import datetime
 
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+        # 300 s: the ranks share the host cores while they build weights and frames, so they reach the first barrier
+        # at different times; a wedged collective still ends the run instead of burning the box's time limit
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+        dist.barrier()   # bring the communicator up before the CPU-heavy setup
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
     K, Wm = args.steps, args.warmup
 
     # ---- workload: each rank owns a different synthetic match (video-level sharding)
