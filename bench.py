@@ -274,8 +274,9 @@ def run_gpu(args):
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
     K, Wm = args.steps, args.warmup
 
-    # ---- workload: each rank owns a different synthetic match (video-level sharding)
-    boxes = match_boxes(seed=2024 + rank)
+    # ---- workload: each rank owns one synthetic match (video-level sharding)
+    # the same box track on every rank (weak scaling = literally the same work per GPU); pixel content differs by rank
+    boxes = match_boxes(seed=2024)
     px = yolo_pixels_batch(boxes, W, H)
     resident = []
     for b in range(N_RESIDENT):
@@ -348,7 +349,11 @@ def run_gpu(args):
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms_ranks = [ms]
     if world > 1:
+        allms = torch.zeros((world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allms, t)
+        ms_ranks = [float(v) for v in allms.tolist()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * K * BATCH_FRAMES / (ms_max / 1e3)
@@ -469,7 +474,7 @@ def run_gpu(args):
                        "crop": "square_crop(128, padding=30) exact Pillow-bicubic + INTER_AREA chain", "window": "7 frames, delta 3",
                        "weights": "reference architecture, seeded calibrated random init", "precision": args.precision,
                        "l2": f"inputs larger than L2: {N_RESIDENT} resident batches of 1.59 GB cycled", "parallelism": f"dp{world}"},
-            "clocks": clocks,
+            "clocks": clocks, "ms_per_step_by_rank": [m / K for m in ms_ranks],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "mode": e2e_desc, "whole_frames_memcpy": e2e_runs["whole"], "in_place_pinned": e2e_runs["inplace"],
                     "window_staging": e2e_runs["windows"],
