@@ -339,8 +339,8 @@ def run_gpu(args):
     e0.record()
     for i in range(K):
         step(resident[(Wm + i) % N_RESIDENT], slot=i)
-        if rank == 0 and (i % 4 == 2 or i == K - 1):
-            sampler.poll_once()   # the host runs ahead of the GPU: this lands while earlier steps execute
+        if rank == 0 and i == K - 1:
+            sampler.poll_once()   # everything is enqueued and the GPU is still working through it: a free sample
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), lab_local)
     e1.record()

@@ -36,9 +36,11 @@ template <int NA, int NB>
 __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr int NSTAGE = (NA == 1) ? 2 : 1;
-    constexpr int STAGE_BYTES = NA * C1_A_PLANE;
-    uint8_t* sA = smem;                                    // [NSTAGE][NA][7][128 x 64 B]
+    // one stage = the seven (ky) boxes of ONE operand plane; a split-precision tile (NA = 2) takes two consecutive
+    // stages, hi then lo, accumulated into the same TMEM tile -- so both modes run the same two-stage pipeline
+    constexpr int NSTAGE = 2;
+    constexpr int STAGE_BYTES = C1_A_PLANE;
+    uint8_t* sA = smem;                                    // [NSTAGE][7][128 x 64 B]
     uint8_t* sB = smem + NSTAGE * STAGE_BYTES;             // [NB][7][64 x 64 B]
     float* rows = (float*)(sB + NB * C1_B_PLANE);          // [3][64 px][C1_ROW_PITCH] conv rows for the fused max-pool
     uint64_t* bars = (uint64_t*)((uint8_t*)rows + C1_ROWS_BYTES);
@@ -80,22 +82,22 @@ __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps m
             for (int n = blockIdx.x; n < a.n_crops; n += gridDim.x)
             for (int t = 0; t < 32; t++) {   // a CTA walks the tiles of a crop in order (the fused max-pool needs it)
                 const int oy0 = t << 1;
-                mbar_wait(&aempty[st], ph ^ 1);
-                if (elect_one()) {
-                    mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
 #pragma unroll
-                    for (int pl = 0; pl < NA; pl++) {
+                for (int pl = 0; pl < NA; pl++) {
+                    mbar_wait(&aempty[st], ph ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&afull[st], STAGE_BYTES);
 #pragma unroll
                         for (int ky = 0; ky < 7; ky++) {
                             const int dy = ky - 3;           // input row = 2*oy + dy
                             const int py = dy & 1;           // row parity -> which tensor map
                             const int j0 = oy0 + (dy - py) / 2;
-                            tma_load_4d(sA + st * STAGE_BYTES + pl * C1_A_PLANE + ky * C1_A_KY, &maps.a[pl][py], &afull[st], 0, 0, j0, n);
+                            tma_load_4d(sA + st * STAGE_BYTES + ky * C1_A_KY, &maps.a[pl][py], &afull[st], 0, 0, j0, n);
                         }
                     }
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -111,27 +113,28 @@ __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps m
                 const int acc = it & 1;
                 const uint32_t acc_ph = (it >> 1) & 1;
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
-                mbar_wait(&afull[st], ph);
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * C1_COUT;
-                const uint32_t sa0 = smem_u32(sA + st * STAGE_BYTES);
-                if (elect_one()) {
-                    const uint64_t da0 = umma_desc_sw64(sa0), db0 = umma_desc_sw64(sb0);
-                    const uint64_t dal0 = (NA == 2) ? umma_desc_sw64(sa0 + C1_A_PLANE) : 0;
-                    const uint64_t dbl0 = (NB == 2) ? umma_desc_sw64(sb0 + C1_B_PLANE) : 0;
 #pragma unroll
-                    for (int ks = 0; ks < 14; ks++) {
-                        const uint32_t ia = ((ks >> 1) * C1_A_KY + (ks & 1) * 32) >> 4;   // start-address field increments
-                        const uint32_t ib = ((ks >> 1) * C1_B_KY + (ks & 1) * 32) >> 4;
-                        umma_bf16(d_tmem, da0 + ia, db0 + ib, idesc, ks != 0);
-                        if (NA == 2) umma_bf16(d_tmem, dal0 + ia, db0 + ib, idesc, 1);
-                        if (NB == 2) umma_bf16(d_tmem, da0 + ia, dbl0 + ib, idesc, 1);
+                for (int pl = 0; pl < NA; pl++) {            // plane 0: A_hi x (B_hi [+ B_lo]); plane 1: A_lo x B_hi
+                    mbar_wait(&afull[st], ph);
+                    tc_fence_after();
+                    const uint32_t sa0 = smem_u32(sA + st * STAGE_BYTES);
+                    if (elect_one()) {
+                        const uint64_t da0 = umma_desc_sw64(sa0), db0 = umma_desc_sw64(sb0);
+                        const uint64_t dbl0 = (NB == 2) ? umma_desc_sw64(sb0 + C1_B_PLANE) : 0;
+#pragma unroll
+                        for (int ks = 0; ks < 14; ks++) {
+                            const uint32_t ia = ((ks >> 1) * C1_A_KY + (ks & 1) * 32) >> 4;   // start-address field increments
+                            const uint32_t ib = ((ks >> 1) * C1_B_KY + (ks & 1) * 32) >> 4;
+                            umma_bf16(d_tmem, da0 + ia, db0 + ib, idesc, (pl | ks) != 0);
+                            if (NB == 2 && pl == 0) umma_bf16(d_tmem, da0 + ia, dbl0 + ib, idesc, 1);
+                        }
+                        umma_commit(&aempty[st]);
+                        if (pl == NA - 1) umma_commit(&tfull[acc]);
                     }
-                    umma_commit(&aempty[st]);
-                    umma_commit(&tfull[acc]);
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++st == NSTAGE) { st = 0; ph ^= 1; }
             }
         }
     } else {
@@ -198,8 +201,8 @@ __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps m
 template <int NA, int NB>
 static int launch_c1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream) {
     auto kern = conv1_kernel<NA, NB>;
-    constexpr int NSTAGE = (NA == 1) ? 2 : 1;
-    const size_t smem = 1024 + (size_t)NSTAGE * NA * C1_A_PLANE + (size_t)NB * C1_B_PLANE + C1_ROWS_BYTES + 128;
+    constexpr int NSTAGE = 2;
+    const size_t smem = 1024 + (size_t)NSTAGE * C1_A_PLANE + (size_t)NB * C1_B_PLANE + C1_ROWS_BYTES + 128;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PA_ERR_CUDA;

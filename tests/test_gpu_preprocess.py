@@ -240,3 +240,48 @@ def test_match_stream_host_modes_agree(torch_cuda):
         assert torch.equal(outs[mode][2], outs["device"][2])
         assert torch.equal(outs[mode][0], outs["device"][0])
         assert torch.equal(outs[mode][1], outs["device"][1]), mode
+
+
+def test_unaligned_frame_geometry(torch_cuda):
+    """Frames whose rows are not 16-byte multiples (1001 px wide: 3003-byte pitch) and pitched views of wider
+    frames take the byte-granular load paths of pa_preprocess and pa_stage_windows: still bit-exact vs the C oracle."""
+    torch = torch_cuda
+    from oracle import resample
+    from playaid_core_b200 import _lib
+    from playaid_core_b200.preprocess import crop_records, preprocess_crops, stage_windows
+
+    rng = np.random.default_rng(5)
+    Hh, Ww = 477, 1001
+    yy, xx = np.mgrid[0:Hh, 0:Ww]
+    base = np.stack([(xx * 3 + yy) % 256, (xx + yy * 2) % 256, (xx * yy // 7) % 256], -1).astype(np.uint8)
+    frames = np.stack([base, np.roll(base, 37, 1), (rng.integers(0, 256, base.shape)).astype(np.uint8)])
+    n = 160
+    boxes = np.stack([rng.uniform(0.0, 1.0, n), rng.uniform(0.0, 1.0, n), rng.uniform(0.02, 0.5, n), rng.uniform(0.02, 0.7, n)], 1)
+    fids = rng.integers(0, 3, n)
+    out, status = _run_u8(torch, frames, boxes, fids, 30)
+    # a pitched view: the same pixels inside wider rows (row pitch 3072 B = 16-byte multiple, but x offsets are not)
+    wide = torch.zeros((3, Hh, 1024, 3), dtype=torch.uint8, device="cuda")
+    wide[:, :, :Ww] = torch.from_numpy(frames).cuda()
+    view = wide[:, :, :Ww]
+    rec = torch.from_numpy(crop_records(boxes, fids, Ww, Hh)).cuda()
+    out_v, status_v = preprocess_crops(view, rec, 128, 30, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
+    # staging from pinned host frames with the unaligned pitch
+    host = torch.from_numpy(frames).pin_memory()
+    staged = torch.full(tuple(host.shape), 0x5A, dtype=torch.uint8, device="cuda")
+    stage_windows(host, rec, staged, padding=30, frame_base=0)
+    out_s, status_s = preprocess_crops(staged, rec, 128, 30, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
+    torch.cuda.synchronize()
+    bad = []
+    for i in range(n):
+        try:
+            ok, crop = resample.square_crop(frames[fids[i]], tuple(boxes[i]), 128, 30)
+            want = 1 if ok else 0
+        except ZeroDivisionError:
+            crop, want = None, -2
+        if status[i] != want:
+            bad.append((i, "status", int(status[i]), want))
+        elif want == 1 and not np.array_equal(out[i], crop):
+            bad.append((i, "bytes"))
+    assert not bad, bad[:10]
+    assert np.array_equal(status_v.cpu().numpy(), status) and np.array_equal(out_v.cpu().numpy(), out)
+    assert np.array_equal(status_s.cpu().numpy(), status) and np.array_equal(out_s.cpu().numpy(), out)
