@@ -38,6 +38,7 @@ BATCH_FRAMES = 256
 N_FIGHTERS = 2
 MATCH_FRAMES = 10800  # 3 minutes at 60 fps
 H, W = 1080, 1920
+PRIME = 8          # untimed priming steps before the W warm-up steps
 N_RESIDENT = 4  # distinct 256-frame batches kept in HBM and cycled (each 1.59 GB >> 126 MB L2)
 
 # algorithmic work
@@ -321,7 +322,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing
+    # ---- device-resident timing. A fresh box's first launches pay module loading, allocator growth and the clock
+    # ramp; PRIME untimed steps absorb that whatever W the caller asks for (W warm-up steps follow as specified).
+    make_room(PRIME)
+    for i in range(PRIME):
+        step(resident[i % N_RESIDENT])
+    torch.cuda.synchronize()
     make_room(Wm + K)
     for i in range(Wm):
         step(resident[i % N_RESIDENT])
@@ -473,7 +479,7 @@ def run_gpu(args):
                                    "one match per GPU", "batch_frames": BATCH_FRAMES, "fighters": N_FIGHTERS, "resolution": "1920x1080",
                        "crop": "square_crop(128, padding=30) exact Pillow-bicubic + INTER_AREA chain", "window": "7 frames, delta 3",
                        "weights": "reference architecture, seeded calibrated random init", "precision": args.precision,
-                       "l2": f"inputs larger than L2: {N_RESIDENT} resident batches of 1.59 GB cycled", "parallelism": f"dp{world}"},
+                       "l2": f"inputs larger than L2: {N_RESIDENT} resident batches of 1.59 GB cycled", "parallelism": f"dp{world}", "priming_steps": PRIME},
             "clocks": clocks, "ms_per_step_by_rank": [m / K for m in ms_ranks],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                     "mode": e2e_desc, "whole_frames_memcpy": e2e_runs["whole"], "in_place_pinned": e2e_runs["inplace"],

@@ -11,6 +11,7 @@ rebuild without the reference:
                 + the fighter_test.py record (Appendix D1)
   windows.npz   action_sample_from_frame_middle_out (dataset_utils.py:109-138)
   timeline.json load_ground_truth_from_path (timeline.py:204-280) on tests/golden/sample_log.jsonl
+  resformer.npz ResnetTransformerDetector forward (resnet_transformer_detector.py:99-143), seed 0, batch 2 and batch 1
   ai_timeline.json load_timeline_from_ai_output (timeline.py:52-105) on golden_ai_output(): digest + samples
   model.npz     CNNActionDetector(seed 0, default init).forward on a seeded input
                 (models/cnn_action_detector.py:86-92) and the argmax / exp head (ai_runner.py:474-477)
@@ -106,6 +107,28 @@ def gen_ai_timeline():
         json.dump({"n_frames": len(tl), "sha256": hashlib.sha256(blob).hexdigest(),
                    "samples": {str(i): tl[i] for i in (0, 1, 7, 299, 599)}}, f)
     print("ai timeline frames:", len(tl))
+
+
+def gen_resformer():
+    """ResnetTransformerDetector (models/resnet_transformer_detector.py:99-143), seed 0 default init, under the timm
+    shim: log-probs for a batch of 2 and for its first window alone (the encoder attends across the batch)."""
+    import torch
+
+    from oracle import ref_shims
+
+    ref_shims.install()
+    from playaid.anim_ontology import MOVE_TO_CLASS_ID
+    from playaid.models.resnet_transformer_detector import ResnetTransformerDetector
+
+    torch.manual_seed(0)
+    ref = ResnetTransformerDetector(actions=list(MOVE_TO_CLASS_ID.keys()), sequence_length=7).eval()
+    x = torch.rand((2, 7, 3, 128, 128), generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        y2, y1 = ref(x), ref(x[:1])
+    np.savez_compressed(os.path.join(GOLD, "resformer.npz"), logp_b2=y2.numpy(), logp_b1=y1.numpy(),
+                        n_params=sum(p.numel() for p in ref.parameters()), keys=json.dumps(sorted(ref.state_dict().keys())),
+                        freq_encoding=ref.model.freq_encoding.numpy(), torch_version=torch.__version__)
+    print("resformer: logp range", float(y2.min()), float(y2.max()), "batch effect", float((y2[:1] - y1).abs().max()))
 
 
 def main():
@@ -204,6 +227,9 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ai_timeline":   # regenerate only that fixture
         gen_ai_timeline()
+    elif len(sys.argv) > 1 and sys.argv[1] == "resformer":
+        gen_resformer()
     else:
         main()
         gen_ai_timeline()
+        gen_resformer()

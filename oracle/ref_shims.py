@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- import shims that let the *real* reference run in this container.
 
 The reference (/root/reference/playaid) pins third-party packages that are absent here
-(imutils, addict, pytorch_lightning, torchmetrics, albumentations, dictdiffer).
+(imutils, addict, pytorch_lightning, torchmetrics, albumentations, dictdiffer, timm).
 `install()` registers minimal stand-ins in `sys.modules` and puts /root/reference on sys.path so
 that `oracle/gen_golden.py` can import `playaid.fighter`, `playaid.timeline`,
 `playaid.dataset_utils` and `playaid.models.cnn_action_detector` unmodified and record golden
@@ -133,6 +133,20 @@ def install() -> None:
         def forward(self, *a, **k):
             return torch.tensor(0.0)
 
+    def _timm_create_model(name, num_classes=1000, pretrained=False, **kw):
+        # reference resnet_transformer_detector.py:34 asks timm for "resnet50" with num_classes=0 (pooled 2048-d
+        # features). timm's resnet50 is the torchvision v1.5 architecture with the same parameter names; weights
+        # cannot be downloaded here, so the seeded default init stands in.
+        import torchvision
+
+        assert name == "resnet50", name
+        net = torchvision.models.resnet50(weights=None)
+        if num_classes == 0:
+            net.fc = torch.nn.Identity()
+        return net
+
+    if "timm" not in sys.modules:
+        mod("timm", create_model=_timm_create_model)
     if "pytorch_lightning" not in sys.modules:
         mod("pytorch_lightning", LightningModule=LightningModule)
     if "torchmetrics" not in sys.modules:

@@ -116,3 +116,30 @@ def test_model_matches_reference_default_init(golden_dir):
         lp = m(x)
     assert np.allclose(lp.numpy(), g["logp"], atol=2e-5)
     assert torch.argmax(lp, dim=1).tolist() == g["pred"].tolist() == [59, 59, 59]
+
+
+def test_resformer_restatement_matches_reference_golden(golden_dir):
+    """SURVEY 8f rank 2 groundwork: oracle/ref_resformer.py (module composition and the written-out encoder) against
+    log-probs recorded from the reference's ResnetTransformerDetector, incl. its attention across the batch axis."""
+    import json
+    import os
+
+    import torch
+
+    from oracle.ref_resformer import RefResnetTransformerDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+
+    g = np.load(os.path.join(golden_dir, "resformer.npz"))
+    torch.manual_seed(0)
+    m = RefResnetTransformerDetector(ACTIONS, sequence_length=7).eval()
+    assert sorted(m.state_dict().keys()) == json.loads(str(g["keys"]))
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"])
+    assert np.allclose(m.model.freq_encoding.numpy(), g["freq_encoding"], atol=1e-7)
+    x = torch.rand((2, 7, 3, 128, 128), generator=torch.Generator().manual_seed(7))
+    with torch.no_grad():
+        y2, y1 = m(x).numpy(), m(x[:1]).numpy()
+        e2, e1 = m.model.forward_explicit(x).numpy(), m.model.forward_explicit(x[:1]).numpy()
+    assert y2.shape == (2, 7, 63)
+    assert np.abs(y2 - g["logp_b2"]).max() < 2e-5 and np.abs(y1 - g["logp_b1"]).max() < 2e-5
+    assert np.abs(e2 - g["logp_b2"]).max() < 5e-5 and np.abs(e1 - g["logp_b1"]).max() < 5e-5
+    assert np.abs(g["logp_b2"][:1] - g["logp_b1"]).max() > 1e-3      # the batch-composition dependence is real
