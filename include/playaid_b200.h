@@ -154,6 +154,26 @@ int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, 
             int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Second detector: ResnetTransformerDetector / ResFormer, reference
+ * playaid/models/resnet_transformer_detector.py:25-143 -- ResNet-50 features (2048) -> Linear(2048, 247) ->
+ * + 9 time-encoding features -> three post-norm TransformerEncoder layers (d 256, 8 heads, feed-forward 2048)
+ * -> Linear(256, A) -> log_softmax, one output per frame of the window. The handle is a pa_model: tensors are
+ * handed over with pa_model_set_tensor under the checkpoint's keys ("model.resnet.conv1.weight",
+ * "model.transformer.layers.0.self_attn.in_proj_weight", "model.freq_encoding", ...) and released with
+ * pa_model_destroy. The reference builds the encoder with batch_first=False and feeds it [B,S,256], so attention
+ * runs across the B windows of a call, slot by slot; pa_resformer_forward keeps that: its result for a window
+ * depends on the other windows of the same call, exactly as the reference's does on its batch.
+ * crops   16-bit NHWC4P [n_windows*seq][128][136][4] (pa_preprocess output; lo plane behind the hi plane in split
+ *         precisions), window-major: crop index = window * seq + slot
+ * logp    fp32 [n_windows][seq][n_actions]
+ */
+int pa_resformer_create(pa_ctx* ctx, int n_actions, int seq_len, pa_model** out);
+int pa_resformer_finalize(pa_model* m, int precision);
+int pa_resformer_workspace_bytes(const pa_model* m, int n_windows, size_t* bytes);
+int pa_resformer_forward(pa_model* m, const void* crops, int n_windows, float* logp, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/*
  * Single layers (synchronous; scratch allocated and freed inside): one convolution as a tcgen05
  * implicit GEMM on NHWC bf16 activations [n][hin][hin][cin] (cin % 64 == 0, hin in {32,16,8,4,1} for
  * the output), and the fused stem (7x7/s2 conv + scale/shift + ReLU + 3x3/s2 max-pool) on NHWC4P crops

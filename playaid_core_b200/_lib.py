@@ -20,7 +20,8 @@ EXPORTS = [
     "pa_abi_version", "pa_status_string", "pa_last_error", "pa_ctx_create", "pa_ctx_destroy", "pa_preprocess", "pa_stage_windows",
     "pa_model_create", "pa_model_destroy", "pa_model_set_tensor", "pa_model_finalize", "pa_model_precision",
     "pa_model_workspace_bytes", "pa_features", "pa_crop_elems", "pa_head", "pa_launch_count", "pa_conv2d", "pa_stem",
-    "pa_profile_begin", "pa_profile_end",
+    "pa_profile_begin", "pa_profile_end", "pa_resformer_create", "pa_resformer_finalize",
+    "pa_resformer_workspace_bytes", "pa_resformer_forward",
 ]
 
 
@@ -55,6 +56,10 @@ def load() -> ctypes.CDLL:
                                   c.POINTER(c.c_float), c.POINTER(c.c_float), vp, i32, i32, vp, vp]
     lib.pa_stage_windows.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, i32, i32, i32, vp, vp]
     lib.pa_model_create.argtypes = [vp, i32, i32, c.POINTER(vp)]
+    lib.pa_resformer_create.argtypes = [vp, i32, i32, c.POINTER(vp)]
+    lib.pa_resformer_finalize.argtypes = [vp, i32]
+    lib.pa_resformer_workspace_bytes.argtypes = [vp, i32, c.POINTER(sz)]
+    lib.pa_resformer_forward.argtypes = [vp, vp, i32, vp, vp, sz, vp]
     lib.pa_model_destroy.argtypes = [vp]
     lib.pa_model_set_tensor.argtypes = [vp, c.c_char_p, vp, c.POINTER(i64), i32]
     lib.pa_model_finalize.argtypes = [vp, i32]

@@ -20,6 +20,7 @@ SOURCES = {
     "conv_patch.cu": [],
     "conv1.cu": [],
     "small_kernels.cu": [],
+    "transformer_kernels.cu": [],
     "pa_api.cu": [],
 }
 COMMON = [

@@ -294,10 +294,26 @@ struct PlanOp {
     const bf16 *pin_hi, *pin_lo;
     bf16 *pout_hi, *pout_lo;
     int pn, ph, pw, pc, pf16;
+    // transformer ops (kinds 10..14: tokens, fp32 -> 16-bit, attention, residual + LayerNorm, log-softmax)
+    const float *fa, *fb, *fg, *fbeta;
+    float* fx;
+    int i0, i1, i2;
+    float eps;
+};
+
+struct TfLayer {   // one post-norm TransformerEncoderLayer
+    ConvLayer in_proj, out_proj, lin1, lin2;
+    float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+    float eps1 = 1e-5f, eps2 = 1e-5f;
 };
 
 struct pa_model {
     pa_ctx* ctx = nullptr;
+    int arch = 0;                  // 0 CNNActionDetector, 1 ResnetTransformerDetector (ResFormer)
+    ConvLayer ffn, cls;            // ResFormer: Linear(2048, hidden), Linear(256, A)
+    std::vector<TfLayer> tf;
+    float* enc = nullptr;          // ResFormer time encoding [seq][256 - hidden]
+    int hidden = 0;
     int n_actions = 0, seq = 0;
     int precision = -1;
     bool ready = false;
@@ -984,3 +1000,5 @@ extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n,
     m.dev_allocs.clear();
     return rc;
 }
+
+#include "resformer.inc"

@@ -145,4 +145,11 @@ struct HeadArgs {
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);
 
+// ---------------------------------------------------------------- ResFormer encoder pieces (transformer_kernels.cu)
+int launch_tokens(const float* ffn, const float* enc, float* x, int T, int S, int hidden, cudaStream_t stream);
+int launch_attention(const float* qkv, bf16* out_hi, bf16* out_lo, int B, int S, int f16, cudaStream_t stream);
+int launch_add_layernorm(float* x, const float* y, const float* gamma, const float* beta, float eps, bf16* out_hi, bf16* out_lo,
+                         int T, int f16, cudaStream_t stream);
+int launch_logsoftmax(float* logits, int T, int A, cudaStream_t stream);
+
 }  // namespace pa

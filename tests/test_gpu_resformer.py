@@ -1,0 +1,111 @@
+"""GPU parity of the second detector, `ResnetTransformerDetector`, through pa_resformer_forward:
+against log-probs recorded from the reference itself (tests/golden/resformer.npz) and against the CPU oracle
+(oracle/ref_resformer.py) on other batches -- including the reference's attention across the batch axis."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# max |dlogp| / max |logp|: fp32-parity mode (split half planes; the floor is the tensor core's fp32 accumulation over
+# 53 convolutions and 13 GEMMs) and the 16-bit mode (north_star: 1e-2)
+TOL_SPLIT = 1e-3
+TOL_HALF = 1e-2
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+
+    assert torch.cuda.is_available()
+    from oracle.ref_resformer import RefResnetTransformerDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+
+    torch.manual_seed(0)
+    oracle = RefResnetTransformerDetector(ACTIONS, sequence_length=7).eval()
+    return torch, oracle
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def _model(torch, oracle, precision):
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.models.resnet_transformer_detector import ResnetTransformerDetector
+
+    m = ResnetTransformerDetector(ACTIONS, sequence_length=7, precision=precision).eval()
+    m.load_state_dict(oracle.state_dict())
+    return m
+
+
+def test_reference_golden_batches(setup, golden_dir):
+    torch, oracle = setup
+    g = np.load(os.path.join(golden_dir, "resformer.npz"))
+    x = torch.rand((2, 7, 3, 128, 128), generator=torch.Generator().manual_seed(7))
+    for prec, tol in (("f16x2", TOL_SPLIT), ("f16", TOL_HALF)):
+        m = _model(torch, oracle, prec)
+        y2 = m(x).cpu().numpy()
+        y1 = m(x[:1]).cpu().numpy()
+        e2, e1 = _rel(y2, g["logp_b2"]), _rel(y1, g["logp_b1"])
+        print(f"{prec}: rel log-prob error vs the reference's own output: batch 2 {e2:.3e}, batch 1 {e1:.3e}")
+        assert y2.shape == (2, 7, 63) and np.isfinite(y2).all()
+        assert e2 < tol and e1 < tol
+        assert np.abs(np.exp(y2).sum(-1) - 1).max() < 1e-4
+    # the batch-axis attention is reproduced: window 0 alone differs from window 0 inside the batch, as in the reference
+    d_ref = g["logp_b2"][:1] - g["logp_b1"]
+    d_gpu = y2[:1] - y1
+    assert np.abs(d_ref).max() > 1e-3 and np.abs(d_gpu - d_ref).max() < 0.25 * np.abs(d_ref).max()
+
+
+def test_larger_batch_vs_oracle(setup):
+    torch, oracle = setup
+    x = torch.rand((9, 7, 3, 128, 128), generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        ref = oracle(x).numpy()
+    m = _model(torch, oracle, "f16x2")
+    y = m(x).cpu().numpy()
+    e = _rel(y, ref)
+    agree = float((y.argmax(-1) == ref.argmax(-1)).mean())
+    print(f"f16x2 batch 9: rel log-prob error {e:.3e}, per-frame argmax agreement {agree:.4f}")
+    assert e < TOL_SPLIT
+    top2 = np.sort(ref, axis=-1)
+    margin = top2[..., -1] - top2[..., -2]
+    ok = margin > 4 * TOL_SPLIT * np.abs(ref).max()
+    assert (y.argmax(-1) == ref.argmax(-1))[ok].all()
+
+
+def test_crops_from_preprocess_feed_the_detector(setup):
+    """pa_preprocess -> pa_resformer_forward without leaving the device: window-major NHWC4P crops."""
+    torch, oracle = setup
+    from oracle import ref_path
+    from playaid_core_b200 import _lib
+    from playaid_core_b200.dataset_utils import window_index_table
+    from playaid_core_b200.fighter import boxes_from_records, yolo_pixels_batch
+    from playaid_core_b200.preprocess import crop_records, preprocess_crops
+    from workloads import synthetic
+
+    n, Hh, Ww = 60, 540, 960
+    recs = synthetic.synth_log_records(n, 2, seed=5)
+    boxes = boxes_from_records([r for f in recs for r in f]).reshape(n, 2, 4)
+    frames = synthetic.synth_frames(np.arange(n), yolo_pixels_batch(boxes, Ww, Hh), H=Hh, W=Ww, device="cuda", seed=3)
+    centres = np.array([28, 30, 31])
+    wf = window_index_table(centres, 7, 3, max_frames=n, min_frame=0)          # [3,7] frame numbers
+    fid = wf.reshape(-1)
+    m = _model(torch, oracle, "f16x2")
+    rec = torch.from_numpy(crop_records(boxes[fid, 0], fid, Ww, Hh)).cuda()      # fighter 0, window-major
+    crops, status = preprocess_crops(frames, rec, 128, 30, swap_rb=True, dtype=m.crop_dtype, layout=_lib.LAYOUT_NHWC4P)
+    assert (status == 1).all()
+    y = m.forward_crops(crops, len(centres)).cpu().numpy()
+    # oracle: the same crops cut on the CPU by the reference's libraries, RGB / 255, through the oracle model
+    f_np = frames.cpu().numpy()
+    xs = []
+    for f in fid:
+        ok, c = ref_path.square_crop_libs(f_np[f], tuple(boxes[f, 0]), 128, 30)
+        assert ok
+        xs.append(ref_path.to_tensor([np.ascontiguousarray(c[..., ::-1])]))   # BGR -> RGB (ai_runner.py:448)
+    x = torch.cat(xs).reshape(len(centres), 7, 3, 128, 128)
+    with torch.no_grad():
+        ref = oracle(x).numpy()
+    assert _rel(y, ref) < TOL_SPLIT
