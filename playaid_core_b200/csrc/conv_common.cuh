@@ -62,11 +62,16 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
         rh0 = rh1 = rl0 = rl1 = make_uint4(0, 0, 0, 0);
         auto load_res = [&](int c0, uint4& a0, uint4& a1, uint4& b0, uint4& b1) {
             if (has_res && row_ok && c0 < BLOCK_N && n_base + c0 + 16 <= args.cout) {
-                const uint4* rp = (const uint4*)(args.res_hi + o_base + c0);
-                a0 = __ldg(rp); a1 = __ldg(rp + 1);
-                if (has_res_lo) {
-                    const uint4* lp = (const uint4*)(args.res_lo + o_base + c0);
-                    b0 = __ldg(lp); b1 = __ldg(lp + 1);
+                if (((o_base + c0) & 15) == 0) {
+                    ldg_nc_256(args.res_hi + o_base + c0, a0, a1);
+                    if (has_res_lo) ldg_nc_256(args.res_lo + o_base + c0, b0, b1);
+                } else {
+                    const uint4* rp = (const uint4*)(args.res_hi + o_base + c0);
+                    a0 = __ldg(rp); a1 = __ldg(rp + 1);
+                    if (has_res_lo) {
+                        const uint4* lp = (const uint4*)(args.res_lo + o_base + c0);
+                        b0 = __ldg(lp); b1 = __ldg(lp + 1);
+                    }
                 }
             }
         };
@@ -149,13 +154,18 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
 #pragma unroll
                             for (int i = 0; i < 8; i++) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
                         }
-                        uint4* op = (uint4*)(args.out_hi + o);
-                        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                        if (SPLIT) {
-                            uint4* lp = (uint4*)(args.out_lo + o);
-                            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
-                            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                        if ((o & 15) == 0) {
+                            stg_256(args.out_hi + o, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+                            if (SPLIT) stg_256(args.out_lo + o, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
+                        } else {
+                            uint4* op = (uint4*)(args.out_hi + o);
+                            op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                            op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                            if (SPLIT) {
+                                uint4* lp = (uint4*)(args.out_lo + o);
+                                lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
+                                lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+                            }
                         }
                     } else {
                         uint16_t* oh = (uint16_t*)args.out_hi;
@@ -202,9 +212,8 @@ __device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfu
         const int64_t o = ((int64_t)tile * CG_BLOCK_M + r) * 64 + c0;
         uint4 rh0 = make_uint4(0, 0, 0, 0), rh1 = rh0, rl0 = rh0, rl1 = rh0;
         if (has_res) {
-            const uint4* rp = (const uint4*)(args.res_hi + o);
-            rh0 = __ldg(rp); rh1 = __ldg(rp + 1);
-            if (has_res_lo) { const uint4* lp = (const uint4*)(args.res_lo + o); rl0 = __ldg(lp); rl1 = __ldg(lp + 1); }
+            ldg_nc_256(args.res_hi + o, rh0, rh1);     // o is a multiple of 16 elements: 32-byte aligned
+            if (has_res_lo) ldg_nc_256(args.res_lo + o, rl0, rl1);
         }
         mbar_wait(&tfull[acc], acc_ph);
         tc_fence_after();
@@ -237,14 +246,8 @@ __device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfu
 #pragma unroll
             for (int i = 0; i < 8; i++) h[i] = pack16x2<F16>(v[2 * i], v[2 * i + 1]);
         }
-        uint4* op = (uint4*)(args.out_hi + o);
-        op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-        op[1] = make_uint4(h[4], h[5], h[6], h[7]);
-        if (SPLIT) {
-            uint4* lp = (uint4*)(args.out_lo + o);
-            lp[0] = make_uint4(l[0], l[1], l[2], l[3]);
-            lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
-        }
+        stg_256(args.out_hi + o, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+        if (SPLIT) stg_256(args.out_lo + o, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
     }
 }
 

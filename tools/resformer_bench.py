@@ -43,7 +43,8 @@ for prec in ("f16", "f16x2"):
         groups[g] = groups.get(g, 0.0) + tms / 4
     res[prec] = {"ms_per_call": ms, "windows_per_s": B / ms * 1e3, "crops_per_s": B * S / ms * 1e3,
                  "resnet50_tflops": B * S * 2.69e9 / (groups.get("ResNet-50 convs", ms) / 1e3) / 1e12,
-                 "ms_by_group": {k: round(v, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1])}}
+                 "ms_by_group": {k: round(v, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1])},
+                 "top_kernels_ms": {k: round(v[1] / 4, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]}}
     if prec == "f16x2":
         yg = y.cpu().numpy()
 torch.set_num_threads(os.cpu_count() or 1)
