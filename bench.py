@@ -95,6 +95,8 @@ class ClockSampler:
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.nvml = pynvml
+            self.poll_once()          # the first NVML queries of a process are slow: pay for them here, not under load
+            self.samples.clear()
         except Exception:
             self.nvml = None
 
@@ -345,11 +347,11 @@ def run_gpu(args):
     e0.record()
     for i in range(K):
         step(resident[(Wm + i) % N_RESIDENT], slot=i)
-        if rank == 0 and i == K - 1:
-            sampler.poll_once()   # everything is enqueued and the GPU is still working through it: a free sample
     if world > 1:
         dist.all_gather_into_tensor(gathered.view(-1), lab_local)
     e1.record()
+    if rank == 0:
+        sampler.poll_once()   # after the closing event is enqueued: the GPU is still working through the queued steps
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
