@@ -89,7 +89,9 @@ int pa_ctx_destroy(pa_ctx* ctx);
  *
  * frames   u8 [n_frames][H][W][3], row pitch `pitch_bytes`, frame stride `frame_stride_bytes`
  * boxes    int32 [n_crops][PA_BOX_STRIDE]
- * out      [n_crops][out][out][3] (NHWC) or [n_crops][3][out][out] (NCHW) of out_dtype.
+ * out      [n_crops][out][out][3] (NHWC), [n_crops][3][out][out] (NCHW), [n_crops][out][out][4] (NHWC4) or
+ *          [n_crops][out][out+8][4] (NHWC4P, 16-bit only: what pa_features / pa_resformer_forward read) of
+ *          out_dtype; the *X2 dtypes write a second ("lo") plane of the same shape behind the first.
  *          PA_DTYPE_U8 ignores mean/std and stores the resampled bytes (square_crop's result).
  *          Crops whose status != PA_CROP_OK are written as zeros.
  * status   int32 [n_crops] or NULL
