@@ -17,6 +17,7 @@ LIB = os.path.join(_HERE, "libplayaid_b200.so")
 SOURCES = {
     "preprocess.cu": ["-fmad=false"],
     "conv_gemm.cu": [],
+    "conv_gemm2.cu": [],
     "conv_patch.cu": [],
     "conv1.cu": [],
     "small_kernels.cu": [],

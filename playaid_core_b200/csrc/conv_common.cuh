@@ -41,7 +41,9 @@ __device__ __forceinline__ uint32_t pack16x2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int BLOCK_N, bool F16, bool SPLIT>
+// PAIR = true: the CTA is one half of a cta_group::2 pair (conv_gemm2.cu). Tiles are walked per cluster, this CTA
+// owns m-tile 2*pm + rank of pair tile pm, and "accumulator drained" is signalled to the LEADER CTA's barrier.
+template <int BLOCK_N, bool F16, bool SPLIT, bool PAIR = false>
 __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
                                          int warp, int lane, int total_tiles) {
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -50,8 +52,11 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
     const bool has_res = args.res_hi != nullptr;
     const bool has_res_lo = args.res_lo != nullptr;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
-        const int mt = tile / args.n_tiles, nt = tile - mt * args.n_tiles;
+    const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int pair_rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+    for (int tile = t_first; tile < total_tiles; tile += t_step, it++) {
+        const int mt0 = tile / args.n_tiles, nt = tile - mt0 * args.n_tiles;
+        const int mt = PAIR ? 2 * mt0 + pair_rank : mt0;
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         const int64_t row = (int64_t)mt * CG_BLOCK_M + r;
@@ -182,7 +187,10 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty[acc], 0);   // the leader's MMA warp waits for both halves
+            else mbar_arrive(&tempty[acc]);
+        }
     }
 }
 

@@ -763,9 +763,16 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.k_per_tap = L.cin;
     a.ho = hout; a.wo = hout;
     op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
-    a.num_stages = patch ? patch_stages : conv_gemm_pick_stages(L.block_n, n_a, n_b);
+    // wide layers: a CTA pair per 256-row tile, each CTA staging half of the weight tile (conv_gemm2.cu)
+    const bool pair = !patch && L.block_n == 256 && n_b == 1 && a.m_tiles >= 2 && getenv("PA_NO_PAIR") == nullptr;
+    if (pair) {
+        rc = make_map_b(ctx, &op.maps.b[1], L.w_hi, L.k_total, L.cout, L.block_n / 2);
+        if (rc != PA_OK) return rc;
+    }
+    a.num_stages = patch ? patch_stages : (pair ? conv_gemm2_pick_stages(L.block_n, n_a) : conv_gemm_pick_stages(L.block_n, n_a, n_b));
     if (a.num_stages < 2) return PA_ERR_UNSUPPORTED;
     if (patch) { op.kind = 4; op.patch_ht = ht; }
+    if (pair) op.kind = 5;
     a.scale = L.scale; a.shift = L.shift;
     a.res_hi = res ? res->hi : nullptr;
     a.res_lo = res ? res->lo : nullptr;
@@ -775,6 +782,13 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.out_f32 = out_f32;
     a.f16 = prec_f16(m->precision) ? 1 : 0;
     return PA_OK;
+}
+
+// launch one planned convolution (kinds 2: 1-CTA GEMM, 4: patch mode, 5: CTA-pair GEMM)
+static int launch_conv_op(pa_ctx* ctx, const PlanOp& op, cudaStream_t st) {
+    if (op.kind == 4) return launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, st);
+    if (op.kind == 5) return launch_conv_gemm2(op.maps, op.args, op.block_n, op.n_a, ctx->num_sms, st);
+    return launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st);
 }
 
 static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat, void* ws, size_t ws_bytes) {
@@ -858,8 +872,7 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
         switch (op.kind) {
             case 0: rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, st); break;
             case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
-            case 2: rc = launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st); break;
-            case 4: rc = launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, st); break;
+            case 2: case 4: case 5: rc = launch_conv_op(ctx, op, st); break;
             case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
         }
         if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "feature kernel launch") : rc;
@@ -896,7 +909,7 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
     const PlanOp& g = m->head_gemm;
     {
         ProfSpan sp(ctx, g.name, st);
-        rc = launch_conv_gemm(g.maps, g.args, g.block_n, g.n_a, g.n_b, ctx->num_sms, st);
+        rc = launch_conv_op(ctx, g, st);
     }
     if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "projection launch") : rc;
     HeadArgs h;
@@ -946,9 +959,7 @@ extern "C" int pa_conv2d(pa_ctx* ctx, const void* in_hi, const void* in_lo, int 
         out.hi = (bf16*)out_hi; out.lo = (bf16*)out_lo;
         PlanOp op;
         rc = plan_conv(&m, L, in, n, res_hi ? &res : nullptr, out_hi ? &out : nullptr, out_f32, op);
-        if (rc == PA_OK) rc = (op.kind == 4)
-            ? launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, (cudaStream_t)stream)
-            : launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, (cudaStream_t)stream);
+        if (rc == PA_OK) rc = launch_conv_op(ctx, op, (cudaStream_t)stream);
         if (rc == PA_OK) {
             ctx->launches += 1;
             cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
