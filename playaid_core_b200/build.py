@@ -19,6 +19,7 @@ SOURCES = {
     "conv_gemm.cu": [],
     "conv_gemm2.cu": [],
     "conv_patch.cu": [],
+    "conv_patch2.cu": [],
     "conv1.cu": [],
     "small_kernels.cu": [],
     "transformer_kernels.cu": [],

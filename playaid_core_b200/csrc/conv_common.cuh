@@ -197,7 +197,7 @@ __device__ __forceinline__ void epilogue(const ConvArgs& args, uint64_t* tfull, 
 // Fast path for the Cout = 64 layers (layer1): one 16-column chunk per warp for the whole kernel, so scale/shift
 // live in registers, the residual is requested before the accumulator is waited for, and the TMEM buffer is
 // handed back to the MMA warp as soon as it has been read (the stores overlap the next tile's MMAs).
-template <bool F16, bool SPLIT>
+template <bool F16, bool SPLIT, bool PAIR = false>
 __device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
                                              int warp, int lane, int total_tiles) {
     const int q = warp & 3;
@@ -214,10 +214,13 @@ __device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfu
     const bool has_res_lo = args.res_lo != nullptr;
     const bool relu = args.relu != 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+    const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int pair_rank = PAIR ? (int)(blockIdx.x & 1) : 0;
+    for (int tile = t_first; tile < total_tiles; tile += t_step, it++) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
-        const int64_t o = ((int64_t)tile * CG_BLOCK_M + r) * 64 + c0;
+        const int mt = PAIR ? 2 * tile + pair_rank : tile;          // total_tiles counts pair tiles in PAIR mode
+        const int64_t o = ((int64_t)mt * CG_BLOCK_M + r) * 64 + c0;
         uint4 rh0 = make_uint4(0, 0, 0, 0), rh1 = rh0, rl0 = rh0, rl1 = rh0;
         if (has_res) {
             ldg_nc_256(args.res_hi + o, rh0, rh1);     // o is a multiple of 16 elements: 32-byte aligned
@@ -229,7 +232,10 @@ __device__ __forceinline__ void epilogue_n64(const ConvArgs& args, uint64_t* tfu
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64 + c0, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(&tempty[acc], 0);
+            else mbar_arrive(&tempty[acc]);
+        }
 #pragma unroll
         for (int i = 0; i < 16; i++) v[i] = fmaf(v[i], sc[i], sh[i]);
         if (has_res) {

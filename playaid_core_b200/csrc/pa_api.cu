@@ -730,8 +730,14 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     bool patch = (L.k == 3 && L.stride == 1 && L.pad == 1 && (hout == 32 || hout == 16) && n_b == 1 && (L.cin % 64) == 0 &&
                   L.cout == L.block_n && getenv("PA_NO_PATCH") == nullptr);
     int patch_stages = 0;
+    bool patch_pair = false;
     if (patch) {
-        patch_stages = conv_patch_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
+        const int64_t m_tiles_ = ((int64_t)N * hout * hout + 127) / 128;
+        if (m_tiles_ >= 2 && getenv("PA_NO_PAIR") == nullptr) {   // CTA pair: half of every weight tile per SM (conv_patch2.cu)
+            patch_stages = conv_patch2_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
+            patch_pair = patch_stages >= 2;
+        }
+        if (!patch_pair) patch_stages = conv_patch_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
         if (patch_stages < 2) patch = false;
     }
     for (int pl = 0; pl < n_a; pl++) {
@@ -765,13 +771,13 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
     // wide layers: a CTA pair per 256-row tile, each CTA staging half of the weight tile (conv_gemm2.cu)
     const bool pair = !patch && L.block_n == 256 && n_b == 1 && a.m_tiles >= 2 && getenv("PA_NO_PAIR") == nullptr;
-    if (pair) {
+    if (pair || (patch && patch_pair)) {
         rc = make_map_b(ctx, &op.maps.b[1], L.w_hi, L.k_total, L.cout, L.block_n / 2);
         if (rc != PA_OK) return rc;
     }
     a.num_stages = patch ? patch_stages : (pair ? conv_gemm2_pick_stages(L.block_n, n_a) : conv_gemm_pick_stages(L.block_n, n_a, n_b));
     if (a.num_stages < 2) return PA_ERR_UNSUPPORTED;
-    if (patch) { op.kind = 4; op.patch_ht = ht; }
+    if (patch) { op.kind = patch_pair ? 6 : 4; op.patch_ht = ht; }
     if (pair) op.kind = 5;
     a.scale = L.scale; a.shift = L.shift;
     a.res_hi = res ? res->hi : nullptr;
@@ -784,10 +790,11 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     return PA_OK;
 }
 
-// launch one planned convolution (kinds 2: 1-CTA GEMM, 4: patch mode, 5: CTA-pair GEMM)
+// launch one planned convolution (kinds 2: 1-CTA GEMM, 4: patch mode, 5: CTA-pair GEMM, 6: CTA-pair patch mode)
 static int launch_conv_op(pa_ctx* ctx, const PlanOp& op, cudaStream_t st) {
     if (op.kind == 4) return launch_conv_patch(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, st);
     if (op.kind == 5) return launch_conv_gemm2(op.maps, op.args, op.block_n, op.n_a, ctx->num_sms, st);
+    if (op.kind == 6) return launch_conv_patch2(op.maps, op.args, op.block_n, op.n_a, op.patch_ht, op.patch_wres, op.patch_smem, ctx->num_sms, st);
     return launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st);
 }
 
@@ -872,7 +879,7 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
         switch (op.kind) {
             case 0: rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, st); break;
             case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
-            case 2: case 4: case 5: rc = launch_conv_op(ctx, op, st); break;
+            case 2: case 4: case 5: case 6: rc = launch_conv_op(ctx, op, st); break;
             case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
         }
         if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "feature kernel launch") : rc;

@@ -105,6 +105,9 @@ size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages);
 int conv_patch_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
 int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
                       int num_sms, cudaStream_t stream);
+int conv_patch2_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
+int launch_conv_patch2(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
+                       int num_sms, cudaStream_t stream);
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b);
 // CTA-pair (cta_group::2) variant for BLOCK_N = 256: maps.b[1] must be the weight map with a BLOCK_N/2-row box
 int conv_gemm2_pick_stages(int block_n, int n_a);
