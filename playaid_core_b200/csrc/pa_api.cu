@@ -283,7 +283,7 @@ struct ConvLayer {
 
 struct PlanOp {
     char name[64];
-    int kind;  // 0 conv1, 1 maxpool, 2 conv gemm, 3 avgpool, 4 conv 3x3 patch mode
+    int kind;  // 0 stem, 2 conv gemm, 3 avgpool, 4 conv 3x3 patch mode, 5/6 their CTA-pair variants, 10..14 transformer pieces
     int patch_ht; bool patch_wres; size_t patch_smem;
     Conv1Args c1;
     Conv1Maps c1maps;
@@ -457,6 +457,16 @@ static void split_weights(const std::vector<float>& w, std::vector<uint16_t>& hi
     }
 }
 
+// stem weights [64][3][7][7] -> [64][256] with k = ky*32 + (kx+1)*4 + c (zeros elsewhere): the K order of conv1.cu's im2col
+static void pack_stem_weights(const float* w, std::vector<float>& packed) {
+    packed.assign((size_t)64 * 256, 0.f);
+    for (int o = 0; o < 64; o++)
+        for (int c = 0; c < 3; c++)
+            for (int ky = 0; ky < 7; ky++)
+                for (int kx = 0; kx < 7; kx++)
+                    packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
+}
+
 // pack [cout][cin][k][k] -> [cout][tap][cin], fold BN (or bias) into scale/shift, upload
 static int prepare_conv(pa_model* m, ConvLayer& L) {
     const HostTensor* w = get_tensor(m, L.w_key, {L.cout, L.cin, L.k, L.k});
@@ -516,12 +526,8 @@ extern "C" int pa_model_finalize(pa_model* m, int precision) {
     {
         const HostTensor* w = get_tensor(m, P + "conv1.weight", {64, 3, 7, 7});
         if (!w) return PA_ERR_MISSING_TENSOR;
-        std::vector<float> packed((size_t)64 * 256, 0.f);
-        for (int o = 0; o < 64; o++)
-            for (int c = 0; c < 3; c++)
-                for (int ky = 0; ky < 7; ky++)
-                    for (int kx = 0; kx < 7; kx++)
-                        packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w->data[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
+        std::vector<float> packed;
+        pack_stem_weights(w->data.data(), packed);
         std::vector<uint16_t> hi, lo;
         split_weights(packed, hi, lo, prec_f16(precision));
         rc = upload(m, hi, (uint16_t**)&m->stem_w_hi); if (rc != PA_OK) return rc;
@@ -878,7 +884,6 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
         ProfSpan sp(ctx, op.name, st);
         switch (op.kind) {
             case 0: rc = launch_conv1(op.c1maps, op.c1, ctx->num_sms, st); break;
-            case 1: rc = launch_maxpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pw, op.pc, op.pf16, st); break;
             case 2: case 4: case 5: case 6: rc = launch_conv_op(ctx, op, st); break;
             case 3: rc = launch_avgpool(op.pin_hi, op.pin_lo, op.pout_hi, op.pout_lo, op.pn, op.ph, op.pc, op.pf16, st); break;
         }
@@ -986,12 +991,8 @@ extern "C" int pa_stem(pa_ctx* ctx, const void* in_hi, const void* in_lo, int n,
     if ((split_w & 1) && !in_lo) return PA_ERR_INVALID_ARG;
     pa_model m;
     layer_model(ctx, split_w, m);
-    std::vector<float> packed((size_t)64 * 256, 0.f);
-    for (int o = 0; o < 64; o++)
-        for (int c = 0; c < 3; c++)
-            for (int ky = 0; ky < 7; ky++)
-                for (int kx = 0; kx < 7; kx++)
-                    packed[(size_t)o * 256 + ky * 32 + (kx + 1) * 4 + c] = w_host[(((size_t)o * 3 + c) * 7 + ky) * 7 + kx];
+    std::vector<float> packed;
+    pack_stem_weights(w_host, packed);
     std::vector<uint16_t> hi, lo;
     split_weights(packed, hi, lo, prec_f16(m.precision));
     std::vector<float> sc(scale_host, scale_host + 64), sh(shift_host, shift_host + 64);

@@ -130,8 +130,6 @@ struct Conv1Args {
 int launch_conv1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStream_t stream);
 
 // ---------------------------------------------------------------- small memory-bound kernels
-int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
-                   int f16, cudaStream_t stream);
 int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hw, int c, int f16,
                    cudaStream_t stream);
 int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int f16, cudaStream_t stream);

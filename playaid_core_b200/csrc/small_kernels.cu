@@ -1,118 +1,13 @@
-// Memory-bound helpers of the classifier: 3x3/s2 max-pool, global average pool, fp32 -> bf16
-// hi/lo split, and the temporal head (window gather + MLP + log-softmax / argmax / confidence).
+// Memory-bound helpers of the classifier: global average pool, fp32 -> 16-bit hi/lo split, and the temporal head (window gather + MLP + log-softmax / argmax / confidence).
 //
-// References: torchvision resnet18.maxpool / avgpool (via playaid/models/cnn_action_detector.py:16,32);
+// (the 3x3/s2 max-pool is fused into the stem kernel, conv1.cu)
+// References: torchvision resnet18.avgpool (via playaid/models/cnn_action_detector.py:16,32);
 // SpatialStreamCNN.cnn1d + classifier (:22-27,37-41); CNNActionDetector.forward log_softmax (:92);
 // AIRunner.action_recognition argmax / exp (playaid/ai_runner.py:474-477).
 #include "pa_internal.cuh"
 #include "ptx.cuh"
 
 namespace pa {
-
-template <bool F16> __device__ __forceinline__ float el_lo(uint32_t w) { return dec16<F16>((uint16_t)(w & 0xFFFF)); }
-template <bool F16> __device__ __forceinline__ float el_hi(uint32_t w) { return dec16<F16>((uint16_t)(w >> 16)); }
-
-// ---------------------------------------------------------------- maxpool 3x3 stride 2 pad 1 (NHWC, C % 8 == 0)
-template <bool F16>
-__global__ void maxpool_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo, bf16* __restrict__ out_hi,
-                               bf16* __restrict__ out_lo, int n, int hin, int win, int c) {
-    const int ho = hin / 2, wo = win / 2, cg = c / 8;
-    const int64_t total = (int64_t)n * ho * wo * cg;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % cg);
-        int64_t p = i / cg;
-        const int ox = (int)(p % wo); p /= wo;
-        const int oy = (int)(p % ho);
-        const int b = (int)(p / ho);
-        float best[8];
-        uint16_t bh[8], bl[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { best[k] = -INFINITY; bh[k] = F16 ? 0xFC00 : 0xFF80; bl[k] = 0; }
-        for (int dy = -1; dy <= 1; dy++) {
-            const int iy = 2 * oy + dy;
-            if (iy < 0 || iy >= hin) continue;
-            for (int dx = -1; dx <= 1; dx++) {
-                const int ix = 2 * ox + dx;
-                if (ix < 0 || ix >= win) continue;
-                const int64_t off = (((int64_t)b * hin + iy) * win + ix) * c + g * 8;
-                const uint4 h = __ldg((const uint4*)(in_hi + off));
-                uint4 l = make_uint4(0, 0, 0, 0);
-                if (in_lo) l = __ldg((const uint4*)(in_lo + off));
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float v0 = el_lo<F16>(hw[k]) + el_lo<F16>(lw[k]), v1 = el_hi<F16>(hw[k]) + el_hi<F16>(lw[k]);
-                    if (v0 > best[2 * k]) { best[2 * k] = v0; bh[2 * k] = (uint16_t)(hw[k] & 0xFFFF); bl[2 * k] = (uint16_t)(lw[k] & 0xFFFF); }
-                    if (v1 > best[2 * k + 1]) { best[2 * k + 1] = v1; bh[2 * k + 1] = (uint16_t)(hw[k] >> 16); bl[2 * k + 1] = (uint16_t)(lw[k] >> 16); }
-                }
-            }
-        }
-        const int64_t o = (((int64_t)b * ho + oy) * wo + ox) * c + g * 8;
-        uint4 oh, ol;
-        oh.x = bh[0] | ((uint32_t)bh[1] << 16); oh.y = bh[2] | ((uint32_t)bh[3] << 16);
-        oh.z = bh[4] | ((uint32_t)bh[5] << 16); oh.w = bh[6] | ((uint32_t)bh[7] << 16);
-        *(uint4*)(out_hi + o) = oh;
-        if (out_lo) {
-            ol.x = bl[0] | ((uint32_t)bl[1] << 16); ol.y = bl[2] | ((uint32_t)bl[3] << 16);
-            ol.z = bl[4] | ((uint32_t)bl[5] << 16); ol.w = bl[6] | ((uint32_t)bl[7] << 16);
-            *(uint4*)(out_lo + o) = ol;
-        }
-    }
-}
-
-// Single-plane fast path: post-ReLU inputs (>= 0), packed 2x16-bit maxima, 16-byte vectors.
-template <bool F16>
-__global__ void maxpool_fast_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int hin, int win, int cg) {
-    const int ho = hin / 2, wo = win / 2;
-    const int64_t total = (int64_t)n * ho * wo * cg;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % cg);
-        int64_t p = i / cg;
-        const int ox = (int)(p % wo); p /= wo;
-        const int oy = (int)(p % ho);
-        const int b = (int)(p / ho);
-        uint32_t m[4] = {0, 0, 0, 0};  // +0.0: valid because every window holds >= 1 non-negative value
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-            const int iy = 2 * oy + dy;
-            if (iy < 0 || iy >= hin) continue;
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                const int ix = 2 * ox + dx;
-                if (ix < 0 || ix >= win) continue;
-                const uint4 v = __ldg(in + (((int64_t)b * hin + iy) * win + ix) * cg + g);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (F16) {
-                        __half2 a = *reinterpret_cast<const __half2*>(&m[k]), c = *reinterpret_cast<const __half2*>(&w[k]);
-                        a = __hmax2(a, c);
-                        m[k] = *reinterpret_cast<uint32_t*>(&a);
-                    } else {
-                        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&m[k]), c = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-                        a = __hmax2(a, c);
-                        m[k] = *reinterpret_cast<uint32_t*>(&a);
-                    }
-                }
-            }
-        }
-        out[(((int64_t)b * ho + oy) * wo + ox) * cg + g] = make_uint4(m[0], m[1], m[2], m[3]);
-    }
-}
-
-int launch_maxpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out_lo, int n, int hin, int win, int c,
-                   int f16, cudaStream_t stream) {
-    const int64_t total = (int64_t)n * (hin / 2) * (win / 2) * (c / 8);
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    if (!in_lo) {  // the stem's ReLU output: single plane, non-negative
-        if (f16) maxpool_fast_kernel<true><<<blocks, 256, 0, stream>>>((const uint4*)in_hi, (uint4*)out_hi, n, hin, win, c / 8);
-        else maxpool_fast_kernel<false><<<blocks, 256, 0, stream>>>((const uint4*)in_hi, (uint4*)out_hi, n, hin, win, c / 8);
-    } else if (f16) maxpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
-    else maxpool_kernel<false><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hin, win, c);
-    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
-}
 
 // ---------------------------------------------------------------- global average pool [n][hw][c] -> [n][c]
 template <bool F16>
