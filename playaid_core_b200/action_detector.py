@@ -59,6 +59,7 @@ class MatchStream:
         self.label = torch.full((n_own, self.F), -1, dtype=torch.int32, device=dev)
         self.prob = torch.zeros((n_own, self.F), dtype=torch.float32, device=dev)
         self.status = torch.zeros((self.N, self.F), dtype=torch.int32, device=dev)
+        self._hs_recorded = False
         self.pushed = 0   # local frames whose features are in the table
         self.labeled = 0  # own frames whose windows have been classified
         # window indices of every own frame as LOCAL frame numbers -- dataset_utils.py:109-138
@@ -70,12 +71,15 @@ class MatchStream:
         idx = wf[:, None, :].astype(np.int64) * self.F + np.arange(self.F)[None, :, None]
         self.win_rows = torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))).to(dev)  # [n_own, F, S]
 
-    def push(self, frames: torch.Tensor) -> tuple[int, int]:
+    def push(self, frames: torch.Tensor, defer_labels: bool = False) -> tuple[int, int]:
         """frames uint8 [n,H,W,3], CUDA or pinned host: local frames [pushed, pushed+n). Returns the [a, b)
         range of own frames (indices into `label`) classified by this call; labels trail the pushed
         frames by the window reach until the last frame arrives. Pinned host frames are not copied
         whole: their crop windows are staged into HBM on the detector's copy stream (overlapping the
-        kernels of the previous chunk), or read in place over PCIe when `det.host_mode == "inplace"`."""
+        kernels of the previous chunk), or read in place over PCIe when `det.host_mode == "inplace"`.
+        `defer_labels=True` leaves the temporal head of this chunk running on the detector's head stream (small,
+        latency-bound kernels that then overlap the next chunk's preprocess); call `wait_labels()` before reading
+        `label` / `logp` / `prob` on the current stream. By default push() orders the current stream after it."""
         det = self.det
         n = int(frames.shape[0])
         f0 = self.pushed
@@ -94,7 +98,24 @@ class MatchStream:
             det._stage_release(slot)
         det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
         self.pushed = f0 + n
-        return self._label_ready()
+        main = torch.cuda.current_stream(det.model._device)
+        hs = det._head_stream_for(main)
+        if not self._hs_recorded:   # allocated on the current stream, also used on the head stream
+            for t in (self.feat, self.logp, self.label, self.prob, self.win_rows):
+                t.record_stream(hs)
+            self._hs_recorded = True
+        det._feat_done.record(main)
+        hs.wait_event(det._feat_done)
+        with torch.cuda.stream(hs):
+            rng = self._label_ready()
+            det._labels_done.record(hs)
+        if not defer_labels:
+            main.wait_event(det._labels_done)
+        return rng
+
+    def wait_labels(self) -> None:
+        """Order the current stream after the last head launched by push(defer_labels=True)."""
+        torch.cuda.current_stream(self.det.model._device).wait_event(self.det._labels_done)
 
     def _label_ready(self) -> tuple[int, int]:
         det = self.det
@@ -139,6 +160,25 @@ class ActionDetector:
         self.host_mode = "stage"
         self._stage_bufs: list[torch.Tensor] | None = None
         self._stage_i = 0
+        self._head_stream: torch.cuda.Stream | None = None
+        self._feat_done = self._labels_done = None
+
+    @property
+    def head_stream(self) -> torch.cuda.Stream:
+        """The side stream the temporal head runs on. Work that consumes labels of `push(defer_labels=True)` can be
+        queued there (it is ordered after the head); `torch.cuda.current_stream().wait_stream(det.head_stream)` joins."""
+        return self._head_stream_for(torch.cuda.current_stream(self.model._device))
+
+    def _head_stream_for(self, main: torch.cuda.Stream) -> torch.cuda.Stream:
+        if self._head_stream is None:
+            dev = self.model._device
+            self._head_stream = torch.cuda.Stream(dev)
+            self._feat_done, self._labels_done = torch.cuda.Event(), torch.cuda.Event()
+            # everything queued so far (feature table zero-fill, uploads) precedes the first head
+            first = torch.cuda.Event()
+            first.record(main)
+            self._head_stream.wait_event(first)
+        return self._head_stream
 
     def _stage(self, host_frames: torch.Tensor, rec: torch.Tensor, frame_base: int):
         dev = self.model._device

@@ -71,6 +71,7 @@ class CNNActionDetector:
         self._ctx = None
         self._handle = None
         self._ws: torch.Tensor | None = None
+        self._ws_head: torch.Tensor | None = None
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, state_dict, strict: bool = True):
@@ -202,7 +203,12 @@ class CNNActionDetector:
         logp = torch.empty((n_win, self.num_actions), dtype=torch.float32, device=feat.device)
         label = torch.empty((n_win,), dtype=torch.int32, device=feat.device)
         prob = torch.empty((n_win,), dtype=torch.float32, device=feat.device)
-        ws = self._workspace(max(n_feat, 1))
+        # its own workspace: the head of one chunk may run on a side stream while pa_features of the next chunk uses the other
+        need = ctypes.c_size_t()
+        _lib.check(self._ctx.lib.pa_model_workspace_bytes(self._handle, max(n_feat, 1), ctypes.byref(need)), self._ctx.handle, "workspace_bytes")
+        if self._ws_head is None or self._ws_head.numel() < need.value:
+            self._ws_head = torch.empty((need.value,), dtype=torch.uint8, device=self._device)
+        ws = self._ws_head
         with torch.cuda.device(feat.device):
             rc = self._ctx.lib.pa_head(self._handle, feat.data_ptr(), n_feat, win_idx.data_ptr(), n_win, logp.data_ptr(),
                                        label.data_ptr(), prob.data_ptr(), ws.data_ptr(), ws.numel(),

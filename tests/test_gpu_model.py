@@ -238,3 +238,9 @@ def test_chunking_and_frame_sharding_are_invisible(setup):
         assert torch.equal(torch.cat(labels), whole["label"]), world
         assert torch.equal(torch.cat(logps), whole["logp"]), world
     assert len(set(whole["label"].flatten().tolist())) >= 5   # the calibrated net spreads its predictions
+    # deferred labels: the head of every chunk stays on the detector's side stream; joined once at the end
+    st = det.stream(boxes, 1080, 1920)
+    for s0 in range(0, N, 48):
+        st.push(frames[s0 : s0 + 48], defer_labels=True)
+    torch.cuda.current_stream().wait_stream(det.head_stream)
+    assert torch.equal(st.label, whole["label"]) and torch.equal(st.logp, whole["logp"])
