@@ -8,8 +8,11 @@
  *
  * Conventions: every function returns an int status (PA_OK == 0, negative == error, never
  * throws / exits); pointers are caller-owned DEVICE pointers unless marked "host"; every launch
- * takes an explicit CUDA stream (cudaStream_t passed as void*); no allocation happens after
- * pa_model_finalize() except lazily cached TMA descriptors (host memory).
+ * takes an explicit CUDA stream (cudaStream_t passed as void*). Device allocations: weights in pa_model_finalize();
+ * pa_preprocess / pa_stage_windows keep their scratch (per-crop geometry, coefficient tables, counters) PER STREAM,
+ * sized for 1024 crops on a stream's first call and re-allocated (cudaMalloc + cudaFree: a device synchronisation) only
+ * when a call brings more crops than any earlier call on that stream -- calls on different streams or from different
+ * threads never share scratch. Nothing else allocates (TMA descriptors are cached in host memory).
  */
 #ifndef PLAYAID_B200_H
 #define PLAYAID_B200_H
@@ -21,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 
 /* status codes */
 #define PA_OK 0
@@ -45,6 +48,9 @@ extern "C" {
 #define PA_DTYPE_BF16X2 3 /* bf16 hi plane followed by a bf16 lo (rounding residual) plane */
 #define PA_DTYPE_F16 4    /* IEEE half */
 #define PA_DTYPE_F16X2 5  /* half hi plane followed by a half lo (rounding residual) plane */
+#define PA_DTYPE_BF16_U8 6 /* the resampled BYTE VALUE 0..255 itself as bfloat16 (exact): no /255, mean/std ignored */
+#define PA_DTYPE_F16_U8 7  /* the same as IEEE half (exact); what pa_features_u8 reads: the classifier's stem applies 1/255
+                              in its fp32 epilogue, so the 16-bit input carries no rounding error and needs no lo plane */
 #define PA_LAYOUT_NHWC 0
 #define PA_LAYOUT_NCHW 1
 #define PA_LAYOUT_NHWC4 2 /* 4 channels per pixel, channel 3 == 0 */
@@ -140,6 +146,12 @@ int pa_model_workspace_bytes(const pa_model* m, int n_crops, size_t* bytes);
  */
 int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace,
                 size_t workspace_bytes, void* stream);
+/* Same for crops that hold the raw byte values (pa_preprocess out_dtype PA_DTYPE_F16_U8 / PA_DTYPE_BF16_U8, one plane in
+ * every precision): x = v / 255 of ai_runner.py:463 is folded into the stem's fp32 scale, which equals the reference's
+ * conv(fl(v / 255)) to fp32 rounding and removes the 16-bit rounding of the input (the largest single error source of
+ * the one-product modes) and the stem's second product in the split modes. Only valid for mean 0 / std 1. */
+int pa_features_u8(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace,
+                   size_t workspace_bytes, void* stream);
 /* Elements (of out_dtype) per crop in the internal conv-ready layout. */
 size_t pa_crop_elems(int out_size);
 
@@ -149,11 +161,15 @@ size_t pa_crop_elems(int out_size);
  * feat      fp32 [n_feat][1000]
  * win_idx   int32 [n_win][seq_len] rows of feat (action_sample_from_frame_middle_out,
  *           playaid/dataset_utils.py:109-138, already offset into feat)
+ * feat_status int32 [n_feat] per-crop status as written by pa_preprocess, or NULL. A window with a slot whose
+ *           crop is not PA_CROP_OK gets label -1 and conf 0 (its log-probs are still written): the reference never
+ *           classifies such a window -- process_pairing skips the crop (gen_gt_action_detection.py:54-56) and
+ *           AIRunner asserts on the missing file (ai_runner.py:447)
  * logp      fp32 [n_win][n_actions]; label int32 [n_win]; conf fp32 [n_win] (probability;
  *           AIRunner multiplies by 100.0 on the host)
  */
-int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, int n_win, float* logp,
-            int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream);
+int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* feat_status, const int32_t* win_idx, int n_win,
+            float* logp, int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Second detector: ResnetTransformerDetector / ResFormer, reference

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libplayaid_b200.so")
 
 PA_OK = 0
 CROP_OK, CROP_INVALID, CROP_ZERO_DIV, CROP_TOO_LARGE = 1, 0, -2, -7
-DTYPE_U8, DTYPE_BF16, DTYPE_F32, DTYPE_BF16X2, DTYPE_F16, DTYPE_F16X2 = 0, 1, 2, 3, 4, 5
+DTYPE_U8, DTYPE_BF16, DTYPE_F32, DTYPE_BF16X2, DTYPE_F16, DTYPE_F16X2, DTYPE_BF16_U8, DTYPE_F16_U8 = 0, 1, 2, 3, 4, 5, 6, 7
 LAYOUT_NHWC, LAYOUT_NCHW, LAYOUT_NHWC4, LAYOUT_NHWC4P = 0, 1, 2, 3
 PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_F16, PREC_F16X2, PREC_F16X3 = 0, 1, 2, 3, 4, 5
 BOX_STRIDE = 8
@@ -19,7 +19,7 @@ BOX_STRIDE = 8
 EXPORTS = [
     "pa_abi_version", "pa_status_string", "pa_last_error", "pa_ctx_create", "pa_ctx_destroy", "pa_preprocess", "pa_stage_windows",
     "pa_model_create", "pa_model_destroy", "pa_model_set_tensor", "pa_model_finalize", "pa_model_precision",
-    "pa_model_workspace_bytes", "pa_features", "pa_crop_elems", "pa_head", "pa_launch_count", "pa_conv2d", "pa_stem",
+    "pa_model_workspace_bytes", "pa_features", "pa_features_u8", "pa_crop_elems", "pa_head", "pa_launch_count", "pa_conv2d", "pa_stem",
     "pa_profile_begin", "pa_profile_end", "pa_resformer_create", "pa_resformer_finalize",
     "pa_resformer_workspace_bytes", "pa_resformer_forward",
 ]
@@ -66,9 +66,10 @@ def load() -> ctypes.CDLL:
     lib.pa_model_precision.argtypes = [vp]
     lib.pa_model_workspace_bytes.argtypes = [vp, i32, c.POINTER(sz)]
     lib.pa_features.argtypes = [vp, vp, i32, vp, vp, sz, vp]
+    lib.pa_features_u8.argtypes = [vp, vp, i32, vp, vp, sz, vp]
     lib.pa_crop_elems.restype = sz
     lib.pa_crop_elems.argtypes = [i32]
-    lib.pa_head.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp, sz, vp]
+    lib.pa_head.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, sz, vp]
     fp = c.POINTER(c.c_float)
     lib.pa_conv2d.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.pa_stem.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp]

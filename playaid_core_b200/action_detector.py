@@ -89,14 +89,15 @@ class MatchStream:
             frames, slot = det._stage(frames, self.rec[f0 * self.F : (f0 + n) * self.F], f0)
         rec = self.rec[f0 * self.F : (f0 + n) * self.F].clone()
         rec[:, 0] -= f0  # frame index relative to this chunk
+        u8 = det.byte_crops
         crops, _ = preprocess_crops(
             frames, rec, det.output_size, det.padding, swap_rb=True, mean=det.mean, std=det.std,
-            dtype=det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4P, out=det._crop_buffer(n * self.F),
-            status=self.status[f0 : f0 + n].view(-1),
+            dtype=det.model.crop_dtype_u8 if u8 else det.model.crop_dtype, layout=_lib.LAYOUT_NHWC4P,
+            out=det._crop_buffer(n * self.F), status=self.status[f0 : f0 + n].view(-1),
         )
         if slot is not None:
             det._stage_release(slot)
-        det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F])
+        det.model.features(crops, out=self.feat[f0 * self.F : (f0 + n) * self.F], u8=u8)
         self.pushed = f0 + n
         main = torch.cuda.current_stream(det.model._device)
         hs = det._head_stream_for(main)
@@ -126,7 +127,10 @@ class MatchStream:
         wf = self.win_frames[a:b]
         lo, hi = int(wf.min()), int(wf.max()) + 1  # local feature frames the windows [a, b) touch
         idx = (self.win_rows[a:b] - lo * self.F).view(-1, wf.shape[1]).contiguous()
-        logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx)
+        # windows that touch a crop the reference would not have produced (off-screen: process_pairing skips it,
+        # gen_gt_action_detection.py:54-56) are left unlabelled (-1) by the head kernel
+        logp, label, prob = det.model.head(self.feat[lo * self.F : hi * self.F], idx,
+                                           status=self.status.view(-1)[lo * self.F : hi * self.F])
         self.logp[a:b] = logp.view(b - a, self.F, -1)
         self.label[a:b] = label.view(b - a, self.F)
         self.prob[a:b] = prob.view(b - a, self.F)
@@ -145,6 +149,7 @@ class ActionDetector:
         min_frame: int = 0,
         mean=(0.0, 0.0, 0.0),
         std=(1.0, 1.0, 1.0),
+        byte_crops: bool | None = None,
     ):
         self.model = model
         self.output_size = output_size
@@ -153,7 +158,12 @@ class ActionDetector:
         assert self.num_frames_per_sample == model.sequence_length, "window length must equal the Conv1d kernel"
         self.frame_delta = frame_delta
         self.min_frame = min_frame
-        self.mean, self.std = tuple(mean), tuple(std)
+        self.mean, self.std = tuple(float(v) for v in mean), tuple(float(v) for v in std)
+        default_norm = self.mean == (0.0, 0.0, 0.0) and self.std == (1.0, 1.0, 1.0)
+        if byte_crops and not default_norm:
+            raise ValueError("byte-valued crops fold x = v / 255 into the stem: only valid for mean 0 / std 1")
+        # None = automatic: byte-valued crops whenever the reference's own normalisation (no mean / std) is in force
+        self._byte_crops = default_norm if byte_crops is None else bool(byte_crops)
         self._crops: torch.Tensor | None = None
         # pinned-host frames: "stage" = pa_stage_windows on a copy stream into one of two HBM frame buffers,
         # "inplace" = the preprocess kernel reads the pinned memory itself
@@ -206,8 +216,14 @@ class ActionDetector:
     def _stage_release(self, slot: int) -> None:
         self._stage_free[slot].record(torch.cuda.current_stream(self.model._device))
 
+    @property
+    def byte_crops(self) -> bool:
+        """With the reference's normalisation (x = v / 255, no mean / std: ult_action_dataset.py:349-359) the crops keep
+        the byte values and the stem applies 1/255 in fp32: the 16-bit input is exact in every precision."""
+        return self._byte_crops
+
     def _crop_buffer(self, n: int) -> torch.Tensor:
-        planes = 2 if self.model.split else 1
+        planes = 2 if (self.model.split and not self.byte_crops) else 1
         shape = (planes, n, self.output_size, self.output_size + 8, 4) if planes == 2 else (n, self.output_size, self.output_size + 8, 4)
         if self._crops is None or tuple(self._crops.shape) != shape or self._crops.dtype != self.model.act_dtype:
             self._crops = torch.empty(shape, dtype=self.model.act_dtype, device=self.model._device)
@@ -231,7 +247,21 @@ class ActionDetector:
             label = torch.cat([torch.full((pad, st.F), -1, dtype=label.dtype, device=label.device), label])
             logp = torch.cat([torch.zeros((pad,) + tuple(logp.shape[1:]), dtype=logp.dtype, device=logp.device), logp])
             prob = torch.cat([torch.zeros((pad, st.F), dtype=prob.dtype, device=prob.device), prob])
+        self.check_status(st.status)
         return {"label": label, "logp": logp, "prob": prob, "status": st.status}
+
+    @staticmethod
+    def check_status(status: torch.Tensor) -> None:
+        """Raise where the reference raises: a zero-row window makes ImageOps.contain divide by zero
+        (fighter.py:356 lets ZeroDivisionError escape). Off-screen crops (status 0) are not an error: they are
+        skipped like process_pairing skips them, their windows carry label -1."""
+        st = status.detach().cpu().numpy()
+        if (st == _lib.CROP_ZERO_DIV).any():
+            i = int(np.argwhere(st.reshape(-1) == _lib.CROP_ZERO_DIV)[0, 0])
+            raise ZeroDivisionError(f"division by zero in square_crop of crop {i} (zero-size box with padding)")
+        if (st == _lib.CROP_TOO_LARGE).any():
+            i = int(np.argwhere(st.reshape(-1) == _lib.CROP_TOO_LARGE)[0, 0])
+            raise _lib.PlayaidLibraryError(f"crop {i}: window exceeds the preprocess kernel's staging limits")
 
     def classify_shard(self, frames_halo: torch.Tensor, boxes_halo: np.ndarray, halo_lo: int, own: tuple[int, int],
                        total_frames: int, chunk: int = 256) -> dict:
@@ -242,6 +272,7 @@ class ActionDetector:
         st = self.stream(boxes_halo[:n], H, W, frame_offset=halo_lo, total_frames=total_frames, own=own)
         for s in range(0, n, chunk):
             st.push(frames_halo[s : s + chunk])
+        self.check_status(st.status)
         return {"label": st.label, "logp": st.logp, "prob": st.prob, "status": st.status}
 
     def classify_timeline(self, frames: torch.Tensor, timeline, chunk: int = 256) -> dict:

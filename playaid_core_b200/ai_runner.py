@@ -97,6 +97,14 @@ class AIRunner:
         for s in range(0, N, self.chunk):
             st.push(self.frames[s : s + self.chunk])
         label, prob = st.label.cpu().numpy(), st.prob.cpu().numpy()
+        # the reference asserts on every crop it needs ("Failed to get square crop from frame j", ai_runner.py:418-419;
+        # "Failed to get frame", :447): a window that touches a missing crop is an error here too, not a label
+        self.detector.check_status(st.status)
+        status = st.status.cpu().numpy()
+        for fighter in todo:
+            k = self.fighters.index(fighter)
+            bad = np.nonzero(status[:, k] != _lib.CROP_OK)[0]
+            assert bad.size == 0, f"Failed to get square crop from frame {int(bad[0]) + 1} for {fighter}"
         for fighter in todo:
             k = self.fighters.index(fighter)
             per = self.ai_output_data.setdefault(fighter, {})

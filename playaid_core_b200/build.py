@@ -46,7 +46,9 @@ def _deps_mtime() -> float:
     return t
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiment: bool = False) -> str:
+    """`experiment=True` compiles the tuning / debug switches in (-DPA_EXPERIMENT: PA_CONV_DEBUG, PA_NO_PAIR, PA_PP_*, PA_ST_*
+    environment variables); the shipped library ignores them."""
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     objdir = os.path.join(_HERE, "build")
@@ -55,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src, extra in SOURCES.items():
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *COMMON, *extra, *(["-DPA_EXPERIMENT"] if experiment else []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -71,4 +73,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    exp = "--experiment" in sys.argv
+    print(build(force="--force" in sys.argv or exp, verbose="-v" in sys.argv, experiment=exp))

@@ -219,6 +219,7 @@ int launch_conv1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cudaStr
     const int na = a.split_a ? 2 : 1, nb = a.split_w ? 2 : 1;
     if (na == 1 && nb == 1) return launch_c1<1, 1>(maps, a, num_sms, stream);
     if (na == 2 && nb == 1) return launch_c1<2, 1>(maps, a, num_sms, stream);
+    if (na == 1 && nb == 2) return launch_c1<1, 2>(maps, a, num_sms, stream);   // byte-valued crops with split weights
     if (na == 2 && nb == 2) return launch_c1<2, 2>(maps, a, num_sms, stream);
     return PA_ERR_UNSUPPORTED;
 }

@@ -18,7 +18,14 @@ constexpr int CG_THREADS = (CG_FIRST_EPI_WARP + CG_EPI_WARPS) * 32;  // TMA warp
 // the window-staging kernel (1 KB of reserved shared memory each) can stay resident beside a conv CTA.
 inline size_t conv_smem_budget() {
     static size_t v = 0;
-    if (!v) { const char* e = getenv("PA_CONV_SMEM_KB"); v = (size_t)(e ? atoi(e) : 222) * 1024; }
+    if (!v) {
+        int kb = 222;
+#ifdef PA_EXPERIMENT
+        const char* e = getenv("PA_CONV_SMEM_KB");
+        if (e && atoi(e) >= 64 && atoi(e) <= 227) kb = atoi(e);
+#endif
+        v = (size_t)kb * 1024;
+    }
     return v;
 }
 #define PA_CONV_SMEM_BUDGET conv_smem_budget()

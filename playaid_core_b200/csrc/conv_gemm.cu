@@ -190,7 +190,11 @@ static int launch_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cud
 
 int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args_in, int block_n, int n_a, int n_b, int num_sms, cudaStream_t stream) {
     static int dbg = -1;
+#ifdef PA_EXPERIMENT
     if (dbg < 0) { const char* e = getenv("PA_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+#else
+    dbg = 0;   // the debug modes (wrong results by design) exist only in -DPA_EXPERIMENT builds
+#endif
     ConvArgs args = args_in;
     args.debug = dbg;
 #define PA_CG_CASE(BN, A, B) \

@@ -208,7 +208,11 @@ static int launch_p(const ConvMaps& maps, const ConvArgs& args, const PatchGeom&
 int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args_in, int block_n, int n_a, int ht, bool wres, size_t smem,
                       int num_sms, cudaStream_t stream) {
     static int dbg = -1;
+#ifdef PA_EXPERIMENT
     if (dbg < 0) { const char* e = getenv("PA_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+#else
+    dbg = 0;   // the debug modes (wrong results by design) exist only in -DPA_EXPERIMENT builds
+#endif
     ConvArgs args = args_in;
     args.debug = dbg;
     PatchGeom pg;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,14 +19,20 @@ struct pa_ctx {
     int device = 0;
     int num_sms = 148;
     int64_t launches = 0;
-    int* stage_sched = nullptr;   // pa_stage_windows scheduling scratch
     std::string last_error;
     decltype(&cuTensorMapEncodeTiled) encode_tiled = nullptr;
-    int32_t* pp_status = nullptr;  // scratch per-crop status when the caller passes none
-    int pp_status_cap = 0;
-    int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
-    uint8_t* pp_plan = nullptr;    // per-crop geometry + coefficient tables (preprocess_plan_kernel)
-    int pp_plan_cap = 0;
+    // Scratch of pa_preprocess / pa_stage_windows, one set PER STREAM (calls on different streams may overlap on the
+    // device; calls on one stream are ordered by it). Sized for 1024 crops on a stream's first call and grown (one
+    // cudaMalloc + cudaFree, which synchronise the device) only when a call brings more crops than any before it.
+    struct Scratch {
+        int* stage_sched = nullptr;    // pa_stage_windows scheduling counters
+        int32_t* pp_status = nullptr;  // per-crop status when the caller passes none
+        int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
+        uint8_t* pp_plan = nullptr;    // per-crop geometry + coefficient tables (preprocess_plan_kernel)
+        int cap = 0;                   // crops pp_status / pp_plan are sized for
+    };
+    std::map<cudaStream_t, Scratch> scratch;
+    std::mutex scratch_mu;
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { std::string name; cudaEvent_t e0, e1; };
@@ -33,6 +40,20 @@ struct pa_ctx {
 };
 
 static int cuda_fail(pa_ctx* ctx, cudaError_t e, const char* what);
+
+// Experiment switches (PA_NO_PATCH, PA_NO_PAIR, PA_PP_*, PA_CONV_DEBUG, PA_ST_*) are compiled out of the shipped
+// library: they exist only when it is built with -DPA_EXPERIMENT, and are then read once.
+static bool exp_flag(const char* name) {
+#ifdef PA_EXPERIMENT
+    static std::map<std::string, bool> cache;
+    auto it = cache.find(name);
+    if (it == cache.end()) it = cache.emplace(name, getenv(name) != nullptr).first;
+    return it->second;
+#else
+    (void)name;
+    return false;
+#endif
+}
 
 // RAII span: records an event pair around one launch when profiling is on
 struct ProfSpan {
@@ -134,21 +155,46 @@ extern "C" int pa_ctx_create(int device, pa_ctx** out) {
         return PA_ERR_CUDA;
     }
     ctx->encode_tiled = (decltype(&cuTensorMapEncodeTiled))fn;
-    if (cudaMalloc((void**)&ctx->pp_deferred, sizeof(int)) != cudaSuccess) { delete ctx; return PA_ERR_CUDA; }
     *out = ctx;
     return PA_OK;
 }
 
 extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
-    if (ctx && ctx->pp_status) cudaFree(ctx->pp_status);
-    if (ctx && ctx->pp_deferred) cudaFree(ctx->pp_deferred);
-    if (ctx && ctx->pp_plan) cudaFree(ctx->pp_plan);
-    if (ctx && ctx->stage_sched) cudaFree(ctx->stage_sched);
+    if (ctx)
+        for (auto& kv : ctx->scratch) {
+            pa_ctx::Scratch& sc = kv.second;
+            if (sc.pp_status) cudaFree(sc.pp_status);
+            if (sc.pp_deferred) cudaFree(sc.pp_deferred);
+            if (sc.pp_plan) cudaFree(sc.pp_plan);
+            if (sc.stage_sched) cudaFree(sc.stage_sched);
+        }
     delete ctx;
     return PA_OK;
 }
 
 extern "C" int64_t pa_launch_count(pa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static const int kTableStride = 40960;  // int32 per crop (160 KB) of coefficient tables: enough for a full-frame 1080p window
+
+// the calling stream's scratch, sized for at least n_crops
+static int get_scratch(pa_ctx* ctx, cudaStream_t st, int n_crops, pa_ctx::Scratch** out) {
+    std::lock_guard<std::mutex> lock(ctx->scratch_mu);
+    pa_ctx::Scratch& sc = ctx->scratch[st];
+    if (!sc.stage_sched) PA_CUDA(ctx, cudaMalloc((void**)&sc.stage_sched, PA_STAGE_SCHED_INTS * sizeof(int)));
+    if (!sc.pp_deferred) PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_deferred, sizeof(int)));
+    if (sc.cap < n_crops) {
+        if (sc.pp_status) cudaFree(sc.pp_status);
+        if (sc.pp_plan) cudaFree(sc.pp_plan);
+        sc.pp_status = nullptr; sc.pp_plan = nullptr; sc.cap = 0;
+        const int cap = n_crops < 1024 ? 1024 : n_crops;
+        const size_t geom_b = preprocess_geom_bytes();
+        PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_status, (size_t)cap * sizeof(int32_t)));
+        PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_plan, (((size_t)cap * geom_b + 255) & ~(size_t)255) + (size_t)cap * kTableStride * 4));
+        sc.cap = cap;
+    }
+    *out = &sc;
+    return PA_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ preprocess
 extern "C" int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_frames, int H, int W, int64_t pitch_bytes,
@@ -163,8 +209,9 @@ extern "C" int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_f
     p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
     p.n_frames = n_frames; p.H = H; p.W = W; p.pitch = pitch_bytes; p.fstride = frame_stride_bytes;
     p.boxes = boxes; p.n_crops = n_crops; p.padding = padding; p.frame_base = frame_base;
-    if (!ctx->stage_sched) PA_CUDA(ctx, cudaMalloc((void**)&ctx->stage_sched, PA_STAGE_SCHED_INTS * sizeof(int)));
-    p.sched = ctx->stage_sched;
+    pa_ctx::Scratch* sc = nullptr;
+    { int rc = get_scratch(ctx, (cudaStream_t)stream, 0, &sc); if (rc != PA_OK) return rc; }
+    p.sched = sc->stage_sched;
     ProfSpan sp(ctx, "stage_windows", (cudaStream_t)stream);
     if (launch_stage_windows(p, ctx->num_sms, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "stage_windows launch");
     ctx->launches += 1;
@@ -177,7 +224,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
                              int out_layout, int32_t* status, void* stream) {
     if (!ctx || !frames || !boxes || !out || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
     if (out_size <= 0 || out_size > 1024 || padding < 0) return PA_ERR_INVALID_ARG;
-    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16X2 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4P)
+    if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16_U8 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4P)
         return PA_ERR_INVALID_ARG;
     if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
     if (n_crops == 0) return PA_OK;
@@ -192,36 +239,25 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         p.stdv[c] = std3 ? std3[c] : 1.f;
     }
     p.outp = out; p.out_dtype = out_dtype; p.out_layout = out_layout;
+    p.out_f16 = (out_dtype == PA_DTYPE_F16 || out_dtype == PA_DTYPE_F16X2 || out_dtype == PA_DTYPE_F16_U8) ? 1 : 0;
+    p.out_split = (out_dtype == PA_DTYPE_BF16X2 || out_dtype == PA_DTYPE_F16X2) ? 1 : 0;
+    p.out_raw = (out_dtype == PA_DTYPE_BF16_U8 || out_dtype == PA_DTYPE_F16_U8) ? 1 : 0;
     if (out_layout == PA_LAYOUT_NHWC4P && (out_dtype == PA_DTYPE_U8 || out_dtype == PA_DTYPE_F32)) return PA_ERR_UNSUPPORTED;
     const int ch = (out_layout == PA_LAYOUT_NHWC4 || out_layout == PA_LAYOUT_NHWC4P) ? 4 : 3;
     p.plane_elems = (int64_t)n_crops * out_size * (out_size + (out_layout == PA_LAYOUT_NHWC4P ? 8 : 0)) * ch;
-    if (!status) {
-        if (ctx->pp_status_cap < n_crops) {
-            if (ctx->pp_status) cudaFree(ctx->pp_status);
-            ctx->pp_status = nullptr; ctx->pp_status_cap = 0;
-            PA_CUDA(ctx, cudaMalloc((void**)&ctx->pp_status, (size_t)n_crops * sizeof(int32_t)));
-            ctx->pp_status_cap = n_crops;
-        }
-        status = ctx->pp_status;
-    }
+    pa_ctx::Scratch* sc = nullptr;
+    { int rc = get_scratch(ctx, (cudaStream_t)stream, n_crops, &sc); if (rc != PA_OK) return rc; }
+    if (!status) status = sc->pp_status;
     p.status = status;
     // pass 1: 108 KB of shared memory per 384-thread CTA (2 CTAs / SM) covers the usual fighter windows;
     // pass 2: the few crops that did not fit are redone with the whole carve-out (1 CTA / SM).
     PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
-    PA_CUDA(ctx, cudaMemsetAsync(ctx->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
-    p.deferred = ctx->pp_deferred;
-    // geometry + coefficient tables once per crop (L2-resident scratch owned by the context)
-    const int kTableStride = 40960;  // int32 per crop (160 KB): enough for a full-frame 1080p window
+    PA_CUDA(ctx, cudaMemsetAsync(sc->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
+    p.deferred = sc->pp_deferred;
+    // geometry + coefficient tables once per crop (L2-resident scratch of this stream)
     const size_t geom_b = preprocess_geom_bytes();
-    if (ctx->pp_plan_cap < n_crops) {
-        if (ctx->pp_plan) cudaFree(ctx->pp_plan);
-        ctx->pp_plan = nullptr; ctx->pp_plan_cap = 0;
-        const int cap = n_crops < 1024 ? 1024 : n_crops;
-        PA_CUDA(ctx, cudaMalloc((void**)&ctx->pp_plan, (((size_t)cap * geom_b + 255) & ~(size_t)255) + (size_t)cap * kTableStride * 4));
-        ctx->pp_plan_cap = cap;
-    }
-    p.geoms = ctx->pp_plan;
-    p.tables = (int*)(ctx->pp_plan + (((size_t)ctx->pp_plan_cap * geom_b + 255) & ~(size_t)255));
+    p.geoms = sc->pp_plan;
+    p.tables = (int*)(sc->pp_plan + (((size_t)sc->cap * geom_b + 255) & ~(size_t)255));
     p.table_stride = kTableStride;
     {
         ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
@@ -231,9 +267,14 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     static int cfg_threads = 0, cfg_smem_kb = 0, cfg_xb = 0;
     if (!cfg_threads) {
         const char* e;
+        cfg_threads = 256; cfg_smem_kb = 72; cfg_xb = 0;
+#ifdef PA_EXPERIMENT   // tuning switches exist only in experiment builds (python -m playaid_core_b200.build --experiment)
         cfg_threads = (e = getenv("PA_PP_THREADS")) ? atoi(e) : 256;
         cfg_smem_kb = (e = getenv("PA_PP_SMEM_KB")) ? atoi(e) : 72;
         cfg_xb = (e = getenv("PA_PP_XB")) ? atoi(e) : 0;
+#else
+        (void)e;
+#endif
         if (cfg_threads != 256 && cfg_threads != 384) cfg_threads = 256;
         if (cfg_smem_kb < 48 || cfg_smem_kb > 224) cfg_smem_kb = 72;
     }
@@ -323,6 +364,7 @@ struct pa_model {
     ConvLayer fc, proj;
     float *b1d = nullptr, *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr;
     bf16 *stem_w_hi = nullptr, *stem_w_lo = nullptr;
+    float* stem_scale_u8 = nullptr;   // BN scale / 255: the stem epilogue of pa_features_u8 (crops hold byte values)
     std::vector<void*> dev_allocs;
     // cached forward plan
     std::vector<PlanOp> plan;
@@ -330,6 +372,7 @@ struct pa_model {
     void* plan_ws = nullptr;
     float* plan_feat = nullptr;
     int plan_n = -1;
+    bool plan_u8 = false;
     // cached head plan
     PlanOp head_gemm;
     const float* hplan_feat = nullptr;
@@ -546,6 +589,10 @@ extern "C" int pa_model_finalize(pa_model* m, int precision) {
         }
         rc = upload(m, scale, &L.scale); if (rc != PA_OK) return rc;
         rc = upload(m, shift, &L.shift); if (rc != PA_OK) return rc;
+        // x = v / 255 (ai_runner.py:463) folded into the scale for crops that carry the byte value v itself
+        std::vector<float> scale_u8(64);
+        for (int o = 0; o < 64; o++) scale_u8[o] = (float)((double)g->data[o] / std::sqrt((double)var->data[o] + 1e-5) / 255.0);
+        rc = upload(m, scale_u8, &m->stem_scale_u8); if (rc != PA_OK) return rc;
     }
     // ---- residual stages (execution order per block: conv1, [downsample], conv2)
     const int chans[4] = {64, 128, 256, 512};
@@ -734,12 +781,12 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     else return PA_ERR_UNSUPPORTED;
     // stride-1 3x3 layers on full-width tiles: patch staging (one box of ht+2 rows per horizontal shift)
     bool patch = (L.k == 3 && L.stride == 1 && L.pad == 1 && (hout == 32 || hout == 16) && n_b == 1 && (L.cin % 64) == 0 &&
-                  L.cout == L.block_n && getenv("PA_NO_PATCH") == nullptr);
+                  L.cout == L.block_n && !exp_flag("PA_NO_PATCH"));
     int patch_stages = 0;
     bool patch_pair = false;
     if (patch) {
         const int64_t m_tiles_ = ((int64_t)N * hout * hout + 127) / 128;
-        if (m_tiles_ >= 2 && getenv("PA_NO_PAIR") == nullptr) {   // CTA pair: half of every weight tile per SM (conv_patch2.cu)
+        if (m_tiles_ >= 2 && !exp_flag("PA_NO_PAIR")) {   // CTA pair: half of every weight tile per SM (conv_patch2.cu)
             patch_stages = conv_patch2_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
             patch_pair = patch_stages >= 2;
         }
@@ -776,7 +823,7 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.ho = hout; a.wo = hout;
     op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
     // wide layers: a CTA pair per 256-row tile, each CTA staging half of the weight tile (conv_gemm2.cu)
-    const bool pair = !patch && L.block_n == 256 && n_b == 1 && a.m_tiles >= 2 && getenv("PA_NO_PAIR") == nullptr;
+    const bool pair = !patch && L.block_n == 256 && n_b == 1 && a.m_tiles >= 2 && !exp_flag("PA_NO_PAIR");
     if (pair || (patch && patch_pair)) {
         rc = make_map_b(ctx, &op.maps.b[1], L.w_hi, L.k_total, L.cout, L.block_n / 2);
         if (rc != PA_OK) return rc;
@@ -804,7 +851,7 @@ static int launch_conv_op(pa_ctx* ctx, const PlanOp& op, cudaStream_t st) {
     return launch_conv_gemm(op.maps, op.args, op.block_n, op.n_a, op.n_b, ctx->num_sms, st);
 }
 
-static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat, void* ws, size_t ws_bytes) {
+static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat, void* ws, size_t ws_bytes, bool u8) {
     if (features_ws_bytes(m, n) > ws_bytes) return PA_ERR_WORKSPACE;
     const bool split = prec_split(m->precision);
     const int f16 = prec_f16(m->precision) ? 1 : 0;
@@ -823,8 +870,9 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
     {
         PlanOp op;
         const bf16* in_hi = (const bf16*)crops;
-        const bf16* in_lo = split ? in_hi + (size_t)n * 128 * 136 * 4 : nullptr;
-        int rc = plan_stem(m->ctx, op, in_hi, in_lo, m->stem_w_hi, m->stem_w_lo, m->stem.scale, m->stem.shift, sm[0].hi, sm[0].lo, n, f16);
+        const bf16* in_lo = (split && !u8) ? in_hi + (size_t)n * 128 * 136 * 4 : nullptr;   // byte values are exact: no lo plane
+        int rc = plan_stem(m->ctx, op, in_hi, in_lo, m->stem_w_hi, m->stem_w_lo, u8 ? m->stem_scale_u8 : m->stem.scale, m->stem.shift,
+                           sm[0].hi, sm[0].lo, n, f16);
         if (rc != PA_OK) return rc;
         m->plan.push_back(op);   // conv1 + BN + ReLU + max-pool in one kernel
     }
@@ -865,18 +913,18 @@ static int build_feature_plan(pa_model* m, const void* crops, int n, float* feat
         if (rc != PA_OK) return rc;
         m->plan.push_back(op);
     }
-    m->plan_crops = crops; m->plan_ws = ws; m->plan_feat = feat; m->plan_n = n;
+    m->plan_crops = crops; m->plan_ws = ws; m->plan_feat = feat; m->plan_n = n; m->plan_u8 = u8;
     return PA_OK;
 }
 
-extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+static int features_impl(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace, size_t workspace_bytes, void* stream, bool u8) {
     if (!m || !crops || !feat || !workspace || n_crops <= 0) return PA_ERR_INVALID_ARG;
-    if (!m->ready) return PA_ERR_NOT_READY;
+    if (!m->ready || m->arch != 0) return PA_ERR_NOT_READY;
     pa_ctx* ctx = m->ctx;
     cudaStream_t st = (cudaStream_t)stream;
-    if (m->plan_n != n_crops || m->plan_crops != crops || m->plan_ws != workspace || m->plan_feat != feat) {
+    if (m->plan_n != n_crops || m->plan_crops != crops || m->plan_ws != workspace || m->plan_feat != feat || m->plan_u8 != u8) {
         m->plan_n = -1;
-        int rc = build_feature_plan(m, crops, n_crops, feat, workspace, workspace_bytes);
+        int rc = build_feature_plan(m, crops, n_crops, feat, workspace, workspace_bytes, u8);
         if (rc != PA_OK) return rc;
     }
     for (const PlanOp& op : m->plan) {
@@ -893,8 +941,15 @@ extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* f
     return PA_OK;
 }
 
-extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* win_idx, int n_win, float* logp,
-                       int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int pa_features(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+    return features_impl(m, crops, n_crops, feat, workspace, workspace_bytes, stream, false);
+}
+extern "C" int pa_features_u8(pa_model* m, const void* crops, int n_crops, float* feat, void* workspace, size_t workspace_bytes, void* stream) {
+    return features_impl(m, crops, n_crops, feat, workspace, workspace_bytes, stream, true);
+}
+
+extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t* feat_status, const int32_t* win_idx, int n_win,
+                       float* logp, int32_t* label, float* conf, void* workspace, size_t workspace_bytes, void* stream) {
     if (!m || !feat || !win_idx || !logp || !label || !conf || !workspace || n_feat <= 0 || n_win <= 0) return PA_ERR_INVALID_ARG;
     if (!m->ready) return PA_ERR_NOT_READY;
     pa_ctx* ctx = m->ctx;
@@ -925,7 +980,7 @@ extern "C" int pa_head(pa_model* m, const float* feat, int n_feat, const int32_t
     }
     if (rc != PA_OK) return rc == PA_ERR_CUDA ? cuda_fail(ctx, cudaGetLastError(), "projection launch") : rc;
     HeadArgs h;
-    h.proj = proj; h.win_idx = win_idx; h.n_win = n_win; h.n_feat = n_feat; h.seq = m->seq; h.n_actions = m->n_actions;
+    h.proj = proj; h.feat_status = feat_status; h.win_idx = win_idx; h.n_win = n_win; h.n_feat = n_feat; h.seq = m->seq; h.n_actions = m->n_actions;
     h.b1d = m->b1d; h.w1t = m->w1t; h.b1 = m->b1; h.w2t = m->w2t; h.b2 = m->b2;
     h.logp = logp; h.label = label; h.conf = conf;
     {

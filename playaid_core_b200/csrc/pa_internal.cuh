@@ -23,6 +23,7 @@ struct PPParams {
     float mean[3], stdv[3];
     void* outp;
     int out_dtype, out_layout;
+    int out_f16, out_split, out_raw;  // 16-bit outputs: IEEE half (else bfloat16) / lo plane present / byte value itself (no /255)
     int64_t plane_elems;  // distance between the hi and lo planes (PA_DTYPE_BF16X2)
     int32_t* status;
     int smem_bytes;
@@ -136,6 +137,7 @@ int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int
 
 struct HeadArgs {
     const float* proj;     // [n_feat][seq*512] per-frame temporal projections
+    const int32_t* feat_status;  // [n_feat] per-crop status (PA_CROP_*) or nullptr
     const int32_t* win_idx;  // [n_win][seq]
     int n_win, n_feat, seq, n_actions;
     const float* b1d;      // [512]

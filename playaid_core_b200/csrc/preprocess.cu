@@ -232,8 +232,8 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
         // 16-bit only: [crop][f][dx + 4][4] with zeroed 4-pixel borders
         float fv[3];
         fv[0] = lut[(p.swap_rb ? v2 : v0)]; fv[1] = lut[256 + v1]; fv[2] = lut[512 + (p.swap_rb ? v0 : v2)];
-        const bool f16 = (p.out_dtype == PA_DTYPE_F16 || p.out_dtype == PA_DTYPE_F16X2);
-        const bool split = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2);
+        const bool f16 = p.out_f16 != 0;
+        const bool split = p.out_split != 0;
         uint16_t hi[3], lo[3];
         for (int c = 0; c < 3; c++) {
             if (f16) {
@@ -290,7 +290,7 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
         return;
     }
     // 16-bit float (bf16 or IEEE half), optionally with a lo plane holding the rounding residual
-    const bool f16 = (p.out_dtype == PA_DTYPE_F16 || p.out_dtype == PA_DTYPE_F16X2);
+    const bool f16 = p.out_f16 != 0;
     uint16_t hi[3], lo[3];
     for (int c = 0; c < 3; c++) {
         if (f16) {
@@ -304,7 +304,7 @@ __device__ __forceinline__ void store_pixel(const PPParams& p, const float* lut,
         }
     }
     uint16_t* o = (uint16_t*)p.outp;
-    const bool split = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2);
+    const bool split = p.out_split != 0;
     if (p.out_layout == PA_LAYOUT_NCHW) {
         for (int c = 0; c < 3; c++) {
             int64_t i = (((int64_t)crop * 3 + c) * out + f) * out + dx;
@@ -337,7 +337,7 @@ __device__ void zero_rows(const PPParams& p, int crop, int F0, int F1) {
     int esz = (p.out_dtype == PA_DTYPE_U8) ? 1 : (p.out_dtype == PA_DTYPE_F32 ? 4 : 2);
     int ch = (p.out_layout == PA_LAYOUT_NHWC4 || p.out_layout == PA_LAYOUT_NHWC4P) ? 4 : 3;
     const int wpad = (p.out_layout == PA_LAYOUT_NHWC4P) ? 8 : 0;
-    int nplanes = (p.out_dtype == PA_DTYPE_BF16X2 || p.out_dtype == PA_DTYPE_F16X2) ? 2 : 1;
+    int nplanes = p.out_split ? 2 : 1;
     for (int pl = 0; pl < nplanes; pl++) {
         uint8_t* base = (uint8_t*)p.outp + (int64_t)pl * p.plane_elems * esz;
         if (p.out_layout == PA_LAYOUT_NCHW) {
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPP
     for (int i = tid; i < 768; i += NT) {
         int c = i >> 8, v = i & 255;
         float f = __fdiv_rn((float)v, 255.0f);
-        lut[i] = __fdiv_rn(__fsub_rn(f, p.mean[c]), p.stdv[c]);
+        lut[i] = p.out_raw ? (float)v : __fdiv_rn(__fsub_rn(f, p.mean[c]), p.stdv[c]);
     }
     if (g.tab_ok && p.tables) {
         // copy the slices this slab needs from the crop's precomputed block (preprocess_plan_kernel)
@@ -1188,9 +1188,17 @@ int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream)
     static int unroll = 0, threads = 0, max_sm = 0;
     if (!unroll) {
         const char* e;
+        unroll = 8; threads = ST_THREADS; max_sm = 1 << 20;
+#ifdef PA_EXPERIMENT
         unroll = (e = getenv("PA_ST_UNROLL")) ? atoi(e) : 8;
         threads = (e = getenv("PA_ST_THREADS")) ? atoi(e) : ST_THREADS;
         max_sm = (e = getenv("PA_ST_SMS")) ? atoi(e) : 1 << 20;
+        if (unroll != 2 && unroll != 4) unroll = 8;
+        if (threads < 32 || threads > 1024 || (threads & 31)) threads = ST_THREADS;
+        if (max_sm < 1) max_sm = 1 << 20;
+#else
+        (void)e;
+#endif
         cudaFuncSetAttribute(stage_windows_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(stage_windows_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(stage_windows_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -74,8 +74,19 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
     __shared__ float part[4][128];
     __shared__ float y1[128];
     __shared__ float y2[128];
+    __shared__ int win_ok;
     const int w = blockIdx.x, t = threadIdx.x;
     const int pitch = a.seq * 512;
+    if (t == 0) {   // a window is only classified when every crop it reads exists (see pa_head)
+        int ok = 1;
+        if (a.feat_status)
+            for (int k = 0; k < a.seq; k++) {
+                int f = a.win_idx[(int64_t)w * a.seq + k];
+                f = f < 0 ? 0 : (f >= a.n_feat ? a.n_feat - 1 : f);
+                if (a.feat_status[f] != PA_CROP_OK) ok = 0;
+            }
+        win_ok = ok;
+    }
     {
         const int o = t;
         float s = a.b1d[o];
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
         for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
         const float lse = m + logf(se);
         float best = -INFINITY;
-        int bi = 0x7FFFFFFF;
+        int bi = 0x7FFFFFFF;   // stays there only when every log-prob is NaN: reported as class 0 below
         for (int i = t; i < a.n_actions; i += 32) {
             const float lp = y2[i] - lse;
             a.logp[(int64_t)w * a.n_actions + i] = lp;
@@ -129,8 +140,9 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
         if (t == 0) {
-            a.label[w] = bi;
-            a.conf[w] = expf(best);  // probability; the host multiplies by 100.0 in double like the reference
+            if (bi == 0x7FFFFFFF) bi = 0;   // all-NaN logits: torch.argmax returns the first NaN's index
+            a.label[w] = win_ok ? bi : -1;
+            a.conf[w] = win_ok ? expf(best) : 0.f;  // probability; the host multiplies by 100.0 in double like the reference
         }
     }
 }

@@ -51,7 +51,7 @@ class CNNActionDetector:
         learning_rate: float = 2e-4,
         num_samples: int = 1024,
         freeze_encoder=False,
-        precision: str = "f16",
+        precision: str = "f16x2",
         device=None,
         **kwargs,
     ):
@@ -171,13 +171,20 @@ class CNNActionDetector:
             self._ws = torch.empty((need.value,), dtype=torch.uint8, device=self._device)
         return self._ws
 
-    def features(self, crops: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    @property
+    def crop_dtype_u8(self) -> int:
+        """pa_preprocess out_dtype for byte-valued crops (`features(..., u8=True)`): the resampled byte itself, exact in
+        16 bits, one plane in every precision; the stem applies the 1/255 of ai_runner.py:463 in fp32."""
+        return _lib.DTYPE_F16_U8 if self.half else _lib.DTYPE_BF16_U8
+
+    def features(self, crops: torch.Tensor, out: torch.Tensor | None = None, u8: bool = False) -> torch.Tensor:
         """crops: 16-bit (self.act_dtype) CUDA NHWC4P [n,128,136,4] -- 4 channels (last zero), 4 zero
         pixels either side of every row -- or [2,n,128,136,4] hi/lo planes in split precision, as written by
-        `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4P)` -> fp32 [n,1000]."""
+        `preprocess_crops(dtype=self.crop_dtype, layout=LAYOUT_NHWC4P)` -> fp32 [n,1000].
+        `u8=True`: crops hold byte values 0..255 (`dtype=self.crop_dtype_u8`, always one plane)."""
         if self._handle is None:
             raise _lib.PlayaidLibraryError("no weights loaded: call load_state_dict / load_from_checkpoint first")
-        want = 5 if self.split else 4
+        want = 5 if (self.split and not u8) else 4
         if crops.dtype != self.act_dtype or crops.ndim != want or not crops.is_contiguous() or tuple(crops.shape[-3:]) != (128, 136, 4):
             raise ValueError(f"crops must be contiguous {self.act_dtype} NHWC4P [n,128,136,4] ([2,n,...] planes in split precision)")
         n = int(crops.shape[-4])
@@ -185,14 +192,15 @@ class CNNActionDetector:
             out = torch.empty((n, 1000), dtype=torch.float32, device=crops.device)
         ws = self._workspace(n)
         with torch.cuda.device(crops.device):
-            rc = self._ctx.lib.pa_features(self._handle, crops.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           _lib.current_stream_ptr(crops.device))
+            fn = self._ctx.lib.pa_features_u8 if u8 else self._ctx.lib.pa_features
+            rc = fn(self._handle, crops.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream_ptr(crops.device))
         _lib.check(rc, self._ctx.handle, "pa_features")
         return out
 
-    def head(self, feat: torch.Tensor, win_idx: torch.Tensor):
+    def head(self, feat: torch.Tensor, win_idx: torch.Tensor, status: torch.Tensor | None = None):
         """feat fp32 [n_feat,1000], win_idx int32 [n_win,S] rows of feat ->
-        (logp [n_win,A] fp32, label [n_win] int32, prob [n_win] fp32)."""
+        (logp [n_win,A] fp32, label [n_win] int32, prob [n_win] fp32). `status` int32 [n_feat]: per-crop status
+        of the feature rows (pa_preprocess); windows that touch a crop which is not OK get label -1 / prob 0."""
         if self._handle is None:
             raise _lib.PlayaidLibraryError("no weights loaded")
         if feat.dtype != torch.float32 or not feat.is_contiguous() or feat.shape[-1] != 1000:
@@ -200,6 +208,8 @@ class CNNActionDetector:
         if win_idx.dtype != torch.int32 or not win_idx.is_contiguous() or win_idx.shape[-1] != self.sequence_length:
             raise ValueError("win_idx must be contiguous int32 [n_win, sequence_length]")
         n_feat, n_win = int(feat.shape[0]), int(win_idx.shape[0])
+        if status is not None and (status.dtype != torch.int32 or not status.is_contiguous() or status.numel() != n_feat):
+            raise ValueError("status must be contiguous int32 [n_feat]")
         logp = torch.empty((n_win, self.num_actions), dtype=torch.float32, device=feat.device)
         label = torch.empty((n_win,), dtype=torch.int32, device=feat.device)
         prob = torch.empty((n_win,), dtype=torch.float32, device=feat.device)
@@ -210,7 +220,8 @@ class CNNActionDetector:
             self._ws_head = torch.empty((need.value,), dtype=torch.uint8, device=self._device)
         ws = self._ws_head
         with torch.cuda.device(feat.device):
-            rc = self._ctx.lib.pa_head(self._handle, feat.data_ptr(), n_feat, win_idx.data_ptr(), n_win, logp.data_ptr(),
+            rc = self._ctx.lib.pa_head(self._handle, feat.data_ptr(), n_feat, status.data_ptr() if status is not None else None,
+                                       win_idx.data_ptr(), n_win, logp.data_ptr(),
                                        label.data_ptr(), prob.data_ptr(), ws.data_ptr(), ws.numel(),
                                        _lib.current_stream_ptr(feat.device))
         _lib.check(rc, self._ctx.handle, "pa_head")

@@ -38,7 +38,7 @@ class ResFormer:
 
 class ResnetTransformerDetector:
     def __init__(self, actions: list, batch_size: int = 64, sequence_length: int = 4, learning_rate: float = 2e-4,
-                 num_samples: int = 1024, freeze_encoder=False, precision: str = "f16", device=None, **kwargs):
+                 num_samples: int = 1024, freeze_encoder=False, precision: str = "f16x2", device=None, **kwargs):
         self.learning_rate = learning_rate
         self.batch_size = batch_size
         self.actions = list(actions)

@@ -16,7 +16,8 @@ from . import _lib
 from .fighter import yolo_pixels_batch
 
 _TORCH_DTYPE = {_lib.DTYPE_U8: torch.uint8, _lib.DTYPE_BF16: torch.bfloat16, _lib.DTYPE_F32: torch.float32,
-                _lib.DTYPE_BF16X2: torch.bfloat16, _lib.DTYPE_F16: torch.float16, _lib.DTYPE_F16X2: torch.float16}
+                _lib.DTYPE_BF16X2: torch.bfloat16, _lib.DTYPE_F16: torch.float16, _lib.DTYPE_F16X2: torch.float16,
+                _lib.DTYPE_BF16_U8: torch.bfloat16, _lib.DTYPE_F16_U8: torch.float16}
 
 
 def crop_records(norm_boxes, frame_index, image_width: int, image_height: int) -> np.ndarray:

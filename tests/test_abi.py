@@ -27,7 +27,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_strings(lib):
-    assert lib.pa_abi_version() == 1
+    assert lib.pa_abi_version() == 2
     assert lib.pa_status_string(0) == b"ok" and b"workspace" in lib.pa_status_string(-5)
 
 

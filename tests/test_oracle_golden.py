@@ -143,3 +143,22 @@ def test_resformer_restatement_matches_reference_golden(golden_dir):
     assert np.abs(y2 - g["logp_b2"]).max() < 2e-5 and np.abs(y1 - g["logp_b1"]).max() < 2e-5
     assert np.abs(e2 - g["logp_b2"]).max() < 5e-5 and np.abs(e1 - g["logp_b1"]).max() < 5e-5
     assert np.abs(g["logp_b2"][:1] - g["logp_b1"]).max() > 1e-3      # the batch-composition dependence is real
+
+
+def test_cfg4_slice_golden_labels_give_the_recorded_stats(golden_dir):
+    """BASELINE cfg4 consumer side: the committed fp32-oracle labels of the 2 048-frame slice, through ai_output.yaml ->
+    the REFERENCE's load_timeline_from_ai_output / update_fighters_from_timeline / Stats, reproduce the recorded
+    Stats.stats digests. Needs /root/reference (build container only); the GPU test asserts label identity, which
+    carries this result over to the GPU label stream."""
+    import os
+
+    import pytest
+
+    if not os.path.isdir("/root/reference/playaid"):
+        pytest.skip("reference tree not present")
+    from oracle.gen_cfg4_golden import SLICE, reference_stats_digests, slice_boxes
+
+    g = np.load(os.path.join(golden_dir, "cfg4_slice.npz"))
+    assert g["label"].shape == (SLICE, 2) and len(np.unique(g["label"])) >= 20
+    sha600, sha_slice = reference_stats_digests(g["label"].astype(np.int64), g["prob"], slice_boxes(SLICE))
+    assert sha600 == str(g["stats_sha256_first600"]) and sha_slice == str(g["stats_sha256_slice"])

@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(128) tma_probe(const __grid_constant__ CUtenso
         mbar_arrive_expect_tx(&bar, 64 * 128);
         tma_load_2d(tile, &map, &bar, c0, c1);
     }
-    mbar_wait(&bar, 0);
+    // bounded wait that reports instead of trapping
+    bool done = false;
+    for (int spin = 0; spin < 2000000 && !done; spin++) done = mbar_try_wait(&bar, 0);
+    if (threadIdx.x == 0) out[8192] = done ? 1 : 0;
     for (int i = threadIdx.x; i < 64 * 128; i += 128) out[i] = tile[i];
 }
 
@@ -165,7 +168,7 @@ int main() {
         std::vector<uint8_t> img((size_t)rows * pitch);
         for (int r = 0; r < rows; r++) for (int c = 0; c < pitch; c++) img[(size_t)r * pitch + c] = (uint8_t)((r * 131 + c * 7 + (c >> 8)) & 255);
         uint8_t *dI, *dO;
-        cudaMalloc(&dI, img.size()); cudaMalloc(&dO, 64 * 128);
+        cudaMalloc(&dI, img.size()); cudaMalloc(&dO, 64 * 128 + 16);
         cudaMemcpy(dI, img.data(), img.size(), cudaMemcpyHostToDevice);
         void* fn = nullptr; cudaDriverEntryPointQueryResult q;
         cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
@@ -178,15 +181,16 @@ int main() {
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         printf("tma encode rc=%d\n", (int)rc);
         cudaFuncSetAttribute(tma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 8192);
-        const int cases[4][2] = {{37, 3}, {0, 0}, {5700, 40}, {-5, 10}};
+        const int cases[6][2] = {{0, 0}, {16, 2}, {48, 3}, {5744, 0}, {5696, 40}, {-16, 10}};
         for (auto& cs : cases) {
             const int c0 = cs[0], c1 = cs[1];
             cudaMemset(dO, 0xEE, 8192);
             tma_probe<<<1, 128, 1024 + 8192>>>(map, dO, c0, c1);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("tma_probe: %s\n", cudaGetErrorString(e)); return 1; }
-            std::vector<uint8_t> o(8192);
-            cudaMemcpy(o.data(), dO, 8192, cudaMemcpyDeviceToHost);
+            std::vector<uint8_t> o(8193);
+            cudaMemcpy(o.data(), dO, 8193, cudaMemcpyDeviceToHost);
+            if (!o[8192]) { printf("tma u8 box at (c0=%d, c1=%d): TIMED OUT\n", c0, c1); continue; }
             int bad = 0;
             for (int r = 0; r < 64; r++)
                 for (int b = 0; b < 128; b++) {
