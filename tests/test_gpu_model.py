@@ -187,7 +187,7 @@ def test_ai_runner_facade(tmp_path):
     recs = synthetic.synth_log_records(n, 2, seed=21)
     boxes = boxes_from_records([r for f in recs for r in f]).reshape(n, 2, 4)
     frames = synthetic.synth_frames(np.arange(n), yolo_pixels_batch(boxes, Ww, Hh), H=Hh, W=Ww, device="cuda", seed=9)
-    model = CNNActionDetector(ACTIONS, sequence_length=7, precision="f16", device="cuda").eval()
+    model = CNNActionDetector(ACTIONS, sequence_length=7, device="cuda").eval()   # default precision: the label-exact f16x2
     model.load_state_dict(weights.calibrated_state_dict(0))
     out_file = str(tmp_path / "ai_output.yaml")
     names = ["Byleth", "Diddy Kong"]
@@ -373,7 +373,7 @@ def test_cfg5_dealt_matches_equal_single_pass(setup):
     from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
 
     frames, track = _clip(96, seed=31)
-    segs = [(0, 96), (10, 40), (30, 70), (5, 33), (50, 64), (20, 81), (0, 29)]
+    segs = [(0, 96), (10, 40), (20, 70), (5, 33), (30, 64), (10, 81), (60, 29)]   # (first box-track frame, length)
     lengths = [n for _, n in segs]
     det = ActionDetector(CNNActionDetector(ACTIONS, sequence_length=7).eval().load_state_dict(sd))
 
