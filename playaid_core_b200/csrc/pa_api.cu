@@ -29,7 +29,9 @@ struct pa_ctx {
         int32_t* pp_status = nullptr;  // per-crop status when the caller passes none
         int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
         uint8_t* pp_plan = nullptr;    // per-crop geometry + coefficient tables (preprocess_plan_kernel)
-        int cap = 0;                   // crops pp_status / pp_plan are sized for
+        int2* tc_items = nullptr;      // work items of the tensor-core preprocess kernel
+        int* tc_counters = nullptr;    // [0] enqueued, [1] taken
+        int cap = 0;                   // crops pp_status / pp_plan / tc_items are sized for
     };
     std::map<cudaStream_t, Scratch> scratch;
     std::mutex scratch_mu;
@@ -167,6 +169,8 @@ extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
             if (sc.pp_deferred) cudaFree(sc.pp_deferred);
             if (sc.pp_plan) cudaFree(sc.pp_plan);
             if (sc.stage_sched) cudaFree(sc.stage_sched);
+            if (sc.tc_items) cudaFree(sc.tc_items);
+            if (sc.tc_counters) cudaFree(sc.tc_counters);
         }
     delete ctx;
     return PA_OK;
@@ -182,14 +186,17 @@ static int get_scratch(pa_ctx* ctx, cudaStream_t st, int n_crops, pa_ctx::Scratc
     pa_ctx::Scratch& sc = ctx->scratch[st];
     if (!sc.stage_sched) PA_CUDA(ctx, cudaMalloc((void**)&sc.stage_sched, PA_STAGE_SCHED_INTS * sizeof(int)));
     if (!sc.pp_deferred) PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_deferred, sizeof(int)));
+    if (!sc.tc_counters) PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_counters, 4 * sizeof(int)));
     if (sc.cap < n_crops) {
         if (sc.pp_status) cudaFree(sc.pp_status);
         if (sc.pp_plan) cudaFree(sc.pp_plan);
-        sc.pp_status = nullptr; sc.pp_plan = nullptr; sc.cap = 0;
+        if (sc.tc_items) cudaFree(sc.tc_items);
+        sc.pp_status = nullptr; sc.pp_plan = nullptr; sc.tc_items = nullptr; sc.cap = 0;
         const int cap = n_crops < 1024 ? 1024 : n_crops;
         const size_t geom_b = preprocess_geom_bytes();
         PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_status, (size_t)cap * sizeof(int32_t)));
         PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_plan, (((size_t)cap * geom_b + 255) & ~(size_t)255) + (size_t)cap * kTableStride * 4));
+        PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_items, (size_t)cap * PA_TC_ITEMS_PER_CROP * sizeof(int2)));
         sc.cap = cap;
     }
     *out = &sc;
@@ -259,9 +266,35 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     p.geoms = sc->pp_plan;
     p.tables = (int*)(sc->pp_plan + (((size_t)sc->cap * geom_b + 255) & ~(size_t)255));
     p.table_stride = kTableStride;
+    // Tensor-core path (preprocess_tc.inc): the raw window bytes go from the frame to the tensor core by TMA, which needs
+    // the frames in DEVICE memory with 16-byte aligned rows. Everything else (pinned host frames read in place, unaligned
+    // pitches, crops the plan kernel does not admit) stays on the streaming CUDA-core kernel.
+    CUtensorMap frames_map;
+    p.tc_enable = 0; p.tc_items = sc->tc_items; p.tc_counters = sc->tc_counters;
+    if (!exp_flag("PA_NO_TC") && (pitch_bytes & 15) == 0 && (frame_stride_bytes & 15) == 0 && ((uintptr_t)frames & 15) == 0 &&
+        (int64_t)W * 3 >= 128 && out_size <= 128) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, frames) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+            cuuint64_t dims[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)n_frames};
+            cuuint64_t strides[2] = {(cuuint64_t)pitch_bytes, (cuuint64_t)frame_stride_bytes};
+            cuuint32_t box[3] = {128, 128, 1}, estr[3] = {1, 1, 1};
+            CUresult r = ctx->encode_tiled(&frames_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) p.tc_enable = 1;
+        } else {
+            cudaGetLastError();   // a plain host pointer makes cudaPointerGetAttributes fail on old drivers: not an error here
+        }
+    }
+    PA_CUDA(ctx, cudaMemsetAsync(sc->tc_counters, 0, 4 * sizeof(int), (cudaStream_t)stream));
     {
         ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
         if (launch_preprocess_plan(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess plan launch");
+    }
+    if (p.tc_enable) {
+        ProfSpan sp(ctx, "preprocess_tc", (cudaStream_t)stream);
+        if (launch_preprocess_tc(p, frames_map, ctx->num_sms, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess tc launch");
+        ctx->launches += 1;
     }
     // tunables (defaults measured on B200; PA_PP_* environment variables override for experiments)
     static int cfg_threads = 0, cfg_smem_kb = 0, cfg_xb = 0;

@@ -33,6 +33,9 @@ struct PPParams {
     uint8_t* geoms;       // per-crop geometry written by preprocess_plan_kernel (or nullptr)
     int* tables;          // per-crop coefficient tables, table_stride int32 per crop (or nullptr)
     int table_stride;
+    int tc_enable;        // route eligible crops to the tensor-core kernel (frames in 16-byte aligned device memory)
+    int2* tc_items;       // work items of the tensor-core kernel: {crop, strip | part << 16}
+    int* tc_counters;     // [0] items enqueued by the plan kernel, [1] items taken by the tensor-core kernel
     int threads;          // CTA size of the main kernel: 256 (3 CTAs/SM) or 384 (2 CTAs/SM)
     int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
@@ -68,6 +71,10 @@ struct StageParams {
 constexpr int PA_STAGE_SCHED_INTS = 1 + 256;
 int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream);
 int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);
+// tensor-core kernel over the work items the plan kernel enqueued; frames_map: u8 tensor map {W*3 bytes, H rows, frames},
+// box {128 bytes, 128 rows, 1}, SWIZZLE_128B
+int launch_preprocess_tc(const PPParams& p, const CUtensorMap& frames_map, int num_sms, cudaStream_t stream);
+constexpr int PA_TC_ITEMS_PER_CROP = 512;   // 128 strips x 4 parts at most
 size_t preprocess_geom_bytes();
 
 // ---------------------------------------------------------------- implicit-GEMM convolution (tcgen05 + TMA)

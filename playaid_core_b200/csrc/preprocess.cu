@@ -19,11 +19,21 @@
 // kernel's arithmetic is ~8 integer MACs per source byte, so it is issue-bound, not HBM-bound
 // ("preprocess roofline").
 #include "pa_internal.cuh"
+#include "ptx.cuh"
 
 namespace pa {
 
 constexpr int PP_MAX_THREADS = 384;
 constexpr int PP_SPLIT = 4;
+
+// ---- tensor-core path (preprocess_tc.inc): tile constants shared with the plan kernel
+constexpr int TC_MAX_STRIPS = 128;
+constexpr int TC_NCOLS = 21;         // canvas columns per strip: 21 x 3 channels = 63 <= 64 accumulator columns per digit
+constexpr int TC_TT_ROWS = 512;      // raw rows one work item may span (four 128-row blocks)
+constexpr int TC_XB_FLOATS = 6912;   // fp32 x-pass buffer of one work item (27 KB)
+constexpr int TC_KSPAN = 128;        // bytes of K one coefficient tile covers (one SWIZZLE_128B atom)
+constexpr int TC_MAX_D = 24;         // final columns per strip (x-table slots in shared memory)
+constexpr int TC_XT_CAP = 16;        // area-table entries per final column the strip tables hold (scale_x <= 14)
 
 enum { REG_COPY = 0, REG_FAST = 1, REG_GENERAL = 2, REG_LINEAR = 3 };
 
@@ -42,6 +52,10 @@ struct CropGeom {
     int h_ks, v_ks;
     // per-crop coefficient tables precomputed by preprocess_plan_kernel (int32 offsets into the crop's block)
     int tab_ok, off_h, off_v, off_x, off_y;
+    // routing (preprocess_plan_kernel): 1 = the tensor-core kernel (preprocess_tc.inc) computes this crop as
+    // n_strips x n_parts work items, 0 = the streaming CUDA-core kernel below
+    int route, n_strips, n_parts, rv;
+    uint8_t strip_dx[TC_MAX_STRIPS + 4];   // strip j covers final columns [strip_dx[j], strip_dx[j + 1])
 };
 
 __device__ __forceinline__ double cubic(double x) {
@@ -394,6 +408,96 @@ __device__ __forceinline__ int tab_ksh(const CropGeom& g) { return g.hact ? (g.h
 __device__ __forceinline__ int tab_xcap(const CropGeom& g) { return (g.regime == REG_GENERAL) ? (int)ceil(g.scale_x) + 2 : 0; }
 __device__ __forceinline__ int tab_ycap(const CropGeom& g) { return (g.regime == REG_GENERAL) ? (int)ceil(g.scale_y) + 2 : 2; }
 
+// Rows of the chain one slab of final rows [F0, F1) needs: area rows [a0, a1), canvas rows [s_begin, s_end),
+// resized rows [v_begin, v_end), raw rows [t_begin, t_end) (bounds from the crop's vertical table).
+struct SlabRows { int a0, a1, s_begin, s_end, v_begin, v_end, t_begin, t_end; };
+__device__ void slab_rows(const CropGeom& g, const int* tab, int F0, int F1, SlabRows& q) {
+    q.a0 = max(F0 - g.oy2, 0); q.a1 = min(F1 - g.oy2, g.oh);
+    if (q.a1 < q.a0) q.a1 = q.a0;
+    q.s_begin = q.s_end = q.v_begin = q.v_end = q.t_begin = q.t_end = 0;
+    if (q.a1 > q.a0) {
+        int lo, hi;
+        area_rows(g, q.a0, lo, hi); q.s_begin = lo;
+        area_rows(g, q.a1 - 1, lo, hi); q.s_end = hi;
+        q.v_begin = min(max(q.s_begin - g.oy, 0), g.nh); q.v_end = min(max(q.s_end - g.oy, 0), g.nh);
+        if (q.v_end > q.v_begin) {
+            const int* v_ymin = tab + g.off_v; const int* v_n = v_ymin + g.nh;
+            q.t_begin = v_ymin[q.v_begin];
+            q.t_end = v_ymin[q.v_end - 1] + v_n[q.v_end - 1];
+        }
+    }
+}
+
+// Can the tensor-core kernel take this crop? (both bicubic passes active, general INTER_AREA regime, every tile's taps
+// inside one 128-byte K atom.) If so: cut the final columns into strips and the final rows into parts, and enqueue
+// one work item per (strip, part). Called by one thread after the crop's tables are in global memory.
+__device__ void tc_route(CropGeom& g, const PPParams& p, int crop) {
+    const int out = p.out;
+    if (!(g.pad1 && g.hact && g.vact && g.regime == REG_GENERAL && out <= 128 && g.h_ks <= 8 && g.v_ks <= 16)) return;
+    const int* tab = p.tables + (int64_t)crop * p.table_stride;
+    const int nw = g.nw, nh = g.nh;
+    const int* v_ymin = tab + g.off_v; const int* v_n = v_ymin + nh;
+    const int* h_xmin = tab + g.off_h; const int* h_n = h_xmin + nw;
+    const int xcap = tab_xcap(g);
+    if (xcap > TC_XT_CAP) return;
+    const int* xt_n = tab + g.off_x; const int* xt_si = xt_n + (out + 1);
+    // ---- parts: fewest row slabs whose raw-row span fits the T ring
+    int np = 0, smax = 0;
+    for (int cand = 1; cand <= 4 && !np; cand++) {
+        bool ok = true; int sm = 0;
+        for (int part = 0; part < cand && ok; part++) {
+            SlabRows q;
+            slab_rows(g, tab, (int)((int64_t)part * out / cand), (int)((int64_t)(part + 1) * out / cand), q);
+            if (q.t_end - q.t_begin > TC_TT_ROWS) ok = false;
+            sm = max(sm, q.s_end - q.s_begin);
+        }
+        if (ok) { np = cand; smax = sm; }
+    }
+    if (!np) return;
+    // ---- vertical blocks: rv resized rows whose taps fit one K atom (window start aligned down to 32 raw rows)
+    int rv = 0;
+    for (int cand = 64; cand >= 16 && !rv; cand -= 16) {
+        bool ok = true;
+        for (int part = 0; part < np && ok; part++) {
+            SlabRows q;
+            slab_rows(g, tab, (int)((int64_t)part * out / np), (int)((int64_t)(part + 1) * out / np), q);
+            for (int v0 = q.v_begin; v0 < q.v_end && ok; v0 += cand) {
+                const int vl = min(v0 + cand, q.v_end) - 1;
+                const int kw0 = (v_ymin[v0] - q.t_begin) & ~31;
+                if (v_ymin[vl] + v_n[vl] - q.t_begin - kw0 > TC_KSPAN) ok = false;
+            }
+        }
+        if (ok) rv = cand;
+    }
+    if (!rv) return;
+    // ---- strips of final columns: <= TC_NCOLS canvas columns, horizontal taps inside one K atom, x-pass buffer bound
+    const int dcap = min(smax > 0 ? TC_XB_FLOATS / (3 * smax) : out, TC_MAX_D);
+    if (dcap < 1) return;
+    int ns = 0, dx0 = 0;
+    while (dx0 < out) {
+        if (ns >= TC_MAX_STRIPS) return;
+        const int cx_lo = xt_si[dx0 * xcap];
+        int dx1 = dx0;
+        while (dx1 < out && dx1 - dx0 < dcap) {
+            const int cx_hi = xt_si[dx1 * xcap + xt_n[dx1] - 1] + 1;
+            if (cx_hi - cx_lo > TC_NCOLS) break;
+            const int xx_lo = min(max(cx_lo - g.ox, 0), nw), xx_hi = min(max(cx_hi - g.ox, 0), nw);
+            if (xx_hi > xx_lo) {
+                const int kb0 = ((g.x0 + h_xmin[xx_lo]) * 3) & ~15;
+                if ((g.x0 + h_xmin[xx_hi - 1] + h_n[xx_hi - 1]) * 3 - kb0 > TC_KSPAN) break;
+            }
+            dx1++;
+        }
+        if (dx1 == dx0) return;      // a single column does not fit: leave the crop to the streaming kernel
+        g.strip_dx[ns++] = (uint8_t)dx0;
+        dx0 = dx1;
+    }
+    g.strip_dx[ns] = (uint8_t)out;
+    g.route = 1; g.n_strips = ns; g.n_parts = np; g.rv = rv;
+    const int base = atomicAdd(p.tc_counters, ns * np);
+    for (int i = 0; i < ns * np; i++) p.tc_items[base + i] = make_int2(crop, (i % ns) | ((i / ns) << 16));
+}
+
 // One CTA per crop: geometry + every coefficient table of the crop, once, into global memory
 // (L2-resident), so that the four slab CTAs of the main kernel only copy what they need.
 __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) {
@@ -469,6 +573,12 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
             }
         }
     }
+    __syncthreads();   // the tables written above are read back below (same block: visible after the barrier)
+    if (tid == 0) {
+        g.route = 0; g.n_strips = 0; g.n_parts = 0; g.rv = 0;
+        if (p.tc_enable && g.status == PA_CROP_OK && g.tab_ok) tc_route(g, p, crop);
+    }
+    __syncthreads();
     // publish the geometry (plain words; the main kernel launches after this one on the same stream)
     const int* src = (const int*)&g;
     int* dst = (int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
@@ -494,6 +604,7 @@ __global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPP
         g.tab_ok = 0;
     }
     __syncthreads();
+    if (p.geoms && g.route == 1) return;   // computed by the tensor-core kernel
     const int F0 = (int)((int64_t)part * out / PP_SPLIT), F1 = (int)((int64_t)(part + 1) * out / PP_SPLIT);
     if (g.status != PA_CROP_OK) {
         if (p.first_pass_smem > 0) return;  // reported by the first pass
@@ -1063,6 +1174,8 @@ __global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPP
         __syncthreads();
     }
 }
+
+#include "preprocess_tc.inc"
 
 int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     static bool attr_set = false;

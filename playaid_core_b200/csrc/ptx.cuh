@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 namespace pa {
 
@@ -60,7 +61,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint64_t t0 = global_timer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) { __trap(); }
+        if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) {
+            printf("mbar_wait timeout: block %d thread %d barrier 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
     }
 }
 
