@@ -30,7 +30,7 @@ constexpr int PP_SPLIT = 4;
 constexpr int TC_MAX_STRIPS = 128;
 constexpr int TC_NCOLS = 21;         // canvas columns per strip: 21 x 3 channels = 63 <= 64 accumulator columns per digit
 constexpr int TC_TT_ROWS = 512;      // raw rows one work item may span (four 128-row blocks)
-constexpr int TC_XB_FLOATS = 6912;   // fp32 x-pass buffer of one work item (27 KB)
+constexpr int TC_XB_FLOATS = 7936;   // fp32 x-pass buffer of one work item (31 KB)
 constexpr int TC_KSPAN = 128;        // bytes of K one coefficient tile covers (one SWIZZLE_128B atom)
 constexpr int TC_MAX_D = 24;         // final columns per strip (x-table slots in shared memory)
 constexpr int TC_XT_CAP = 16;        // area-table entries per final column the strip tables hold (scale_x <= 14)
@@ -55,7 +55,7 @@ struct CropGeom {
     // routing (preprocess_plan_kernel): 1 = the tensor-core kernel (preprocess_tc.inc) computes this crop as
     // n_strips x n_parts work items, 0 = the streaming CUDA-core kernel below
     int route, n_strips, n_parts, rv;
-    uint8_t strip_dx[TC_MAX_STRIPS + 4];   // strip j covers final columns [strip_dx[j], strip_dx[j + 1])
+    int off_tc;                            // strip / part records of the tensor-core kernel inside the table block
 };
 
 __device__ __forceinline__ double cubic(double x) {
@@ -411,7 +411,8 @@ __device__ __forceinline__ int tab_ycap(const CropGeom& g) { return (g.regime ==
 // Rows of the chain one slab of final rows [F0, F1) needs: area rows [a0, a1), canvas rows [s_begin, s_end),
 // resized rows [v_begin, v_end), raw rows [t_begin, t_end) (bounds from the crop's vertical table).
 struct SlabRows { int a0, a1, s_begin, s_end, v_begin, v_end, t_begin, t_end; };
-__device__ void slab_rows(const CropGeom& g, const int* tab, int F0, int F1, SlabRows& q) {
+template <typename TY, typename TN>
+__device__ void slab_rows(const CropGeom& g, const TY* v_ymin, const TN* v_n, int F0, int F1, SlabRows& q) {
     q.a0 = max(F0 - g.oy2, 0); q.a1 = min(F1 - g.oy2, g.oh);
     if (q.a1 < q.a0) q.a1 = q.a0;
     q.s_begin = q.s_end = q.v_begin = q.v_end = q.t_begin = q.t_end = 0;
@@ -421,35 +422,42 @@ __device__ void slab_rows(const CropGeom& g, const int* tab, int F0, int F1, Sla
         area_rows(g, q.a1 - 1, lo, hi); q.s_end = hi;
         q.v_begin = min(max(q.s_begin - g.oy, 0), g.nh); q.v_end = min(max(q.s_end - g.oy, 0), g.nh);
         if (q.v_end > q.v_begin) {
-            const int* v_ymin = tab + g.off_v; const int* v_n = v_ymin + g.nh;
-            q.t_begin = v_ymin[q.v_begin];
-            q.t_end = v_ymin[q.v_end - 1] + v_n[q.v_end - 1];
+            q.t_begin = (int)v_ymin[q.v_begin];
+            q.t_end = (int)v_ymin[q.v_end - 1] + (int)v_n[q.v_end - 1];
         }
     }
 }
 
+// What one work item of the tensor-core kernel needs to know about its strip of final columns (8 ints, written by the
+// plan kernel into the crop's table block at off_tc + 8 * strip; the part records, SlabRows, follow at off_tc + 8 * 128)
+struct TcStrip { int dx0, dx1, cx_lo, xx_lo, ncols, kb0, nks_h, pad; };
+
+// Shared-memory copies of the small index tables the routing decision walks (filled while the tables are generated)
+struct PlanScratch {
+    short h_xmin[PA_MAX_WINDOW]; uint8_t h_n[PA_MAX_WINDOW];
+    short v_ymin[PA_MAX_WINDOW]; uint8_t v_n[PA_MAX_WINDOW];
+    short x_first[128], x_last[128];      // first / last canvas column of every final column (area table)
+};
+
 // Can the tensor-core kernel take this crop? (both bicubic passes active, general INTER_AREA regime, every tile's taps
-// inside one 128-byte K atom.) If so: cut the final columns into strips and the final rows into parts, and enqueue
-// one work item per (strip, part). Called by one thread after the crop's tables are in global memory.
-__device__ void tc_route(CropGeom& g, const PPParams& p, int crop) {
+// inside one 128-byte K atom.) If so: cut the final columns into strips and the final rows into parts, write their
+// records, and enqueue one work item per (strip, part). Called by one thread once the crop's tables exist.
+__device__ void tc_route(CropGeom& g, const PPParams& p, int crop, const PlanScratch& ps) {
     const int out = p.out;
     if (!(g.pad1 && g.hact && g.vact && g.regime == REG_GENERAL && out <= 128 && g.h_ks <= 8 && g.v_ks <= 16)) return;
-    const int* tab = p.tables + (int64_t)crop * p.table_stride;
-    const int nw = g.nw, nh = g.nh;
-    const int* v_ymin = tab + g.off_v; const int* v_n = v_ymin + nh;
-    const int* h_xmin = tab + g.off_h; const int* h_n = h_xmin + nw;
-    const int xcap = tab_xcap(g);
-    if (xcap > TC_XT_CAP) return;
-    const int* xt_n = tab + g.off_x; const int* xt_si = xt_n + (out + 1);
+    if (g.rw > PA_MAX_WINDOW || g.rh > PA_MAX_WINDOW) return;
+    int* tab = p.tables + (int64_t)crop * p.table_stride;
+    const int nw = g.nw;
+    if (tab_xcap(g) > TC_XT_CAP) return;
     // ---- parts: fewest row slabs whose raw-row span fits the T ring
     int np = 0, smax = 0;
+    SlabRows parts[4];
     for (int cand = 1; cand <= 4 && !np; cand++) {
         bool ok = true; int sm = 0;
         for (int part = 0; part < cand && ok; part++) {
-            SlabRows q;
-            slab_rows(g, tab, (int)((int64_t)part * out / cand), (int)((int64_t)(part + 1) * out / cand), q);
-            if (q.t_end - q.t_begin > TC_TT_ROWS) ok = false;
-            sm = max(sm, q.s_end - q.s_begin);
+            slab_rows(g, ps.v_ymin, ps.v_n, (int)((int64_t)part * out / cand), (int)((int64_t)(part + 1) * out / cand), parts[part]);
+            if (parts[part].t_end - parts[part].t_begin > TC_TT_ROWS) ok = false;
+            sm = max(sm, parts[part].s_end - parts[part].s_begin);
         }
         if (ok) { np = cand; smax = sm; }
     }
@@ -459,12 +467,11 @@ __device__ void tc_route(CropGeom& g, const PPParams& p, int crop) {
     for (int cand = 64; cand >= 16 && !rv; cand -= 16) {
         bool ok = true;
         for (int part = 0; part < np && ok; part++) {
-            SlabRows q;
-            slab_rows(g, tab, (int)((int64_t)part * out / np), (int)((int64_t)(part + 1) * out / np), q);
+            const SlabRows& q = parts[part];
             for (int v0 = q.v_begin; v0 < q.v_end && ok; v0 += cand) {
                 const int vl = min(v0 + cand, q.v_end) - 1;
-                const int kw0 = (v_ymin[v0] - q.t_begin) & ~31;
-                if (v_ymin[vl] + v_n[vl] - q.t_begin - kw0 > TC_KSPAN) ok = false;
+                const int kw0 = (ps.v_ymin[v0] - q.t_begin) & ~31;
+                if (ps.v_ymin[vl] + ps.v_n[vl] - q.t_begin - kw0 > TC_KSPAN) ok = false;
             }
         }
         if (ok) rv = cand;
@@ -473,26 +480,34 @@ __device__ void tc_route(CropGeom& g, const PPParams& p, int crop) {
     // ---- strips of final columns: <= TC_NCOLS canvas columns, horizontal taps inside one K atom, x-pass buffer bound
     const int dcap = min(smax > 0 ? TC_XB_FLOATS / (3 * smax) : out, TC_MAX_D);
     if (dcap < 1) return;
+    TcStrip* strips = (TcStrip*)(tab + g.off_tc);
     int ns = 0, dx0 = 0;
     while (dx0 < out) {
         if (ns >= TC_MAX_STRIPS) return;
-        const int cx_lo = xt_si[dx0 * xcap];
+        const int cx_lo = ps.x_first[dx0];
         int dx1 = dx0;
+        TcStrip st;
+        st.dx0 = dx0; st.cx_lo = cx_lo; st.xx_lo = 0; st.ncols = 0; st.kb0 = 0; st.nks_h = 0; st.pad = 0;
         while (dx1 < out && dx1 - dx0 < dcap) {
-            const int cx_hi = xt_si[dx1 * xcap + xt_n[dx1] - 1] + 1;
+            const int cx_hi = ps.x_last[dx1] + 1;
             if (cx_hi - cx_lo > TC_NCOLS) break;
             const int xx_lo = min(max(cx_lo - g.ox, 0), nw), xx_hi = min(max(cx_hi - g.ox, 0), nw);
+            int kb0 = 0, kend = 0;
             if (xx_hi > xx_lo) {
-                const int kb0 = ((g.x0 + h_xmin[xx_lo]) * 3) & ~15;
-                if ((g.x0 + h_xmin[xx_hi - 1] + h_n[xx_hi - 1]) * 3 - kb0 > TC_KSPAN) break;
+                kb0 = ((g.x0 + ps.h_xmin[xx_lo]) * 3) & ~15;
+                kend = (g.x0 + ps.h_xmin[xx_hi - 1] + ps.h_n[xx_hi - 1]) * 3 - kb0;
+                if (kend > TC_KSPAN) break;
             }
+            st.xx_lo = xx_lo; st.ncols = xx_hi - xx_lo; st.kb0 = kb0; st.nks_h = (kend + 31) >> 5;
             dx1++;
         }
         if (dx1 == dx0) return;      // a single column does not fit: leave the crop to the streaming kernel
-        g.strip_dx[ns++] = (uint8_t)dx0;
+        st.dx1 = dx1;
+        strips[ns++] = st;
         dx0 = dx1;
     }
-    g.strip_dx[ns] = (uint8_t)out;
+    SlabRows* prec = (SlabRows*)(tab + g.off_tc + 8 * TC_MAX_STRIPS);
+    for (int i = 0; i < np; i++) prec[i] = parts[i];
     g.route = 1; g.n_strips = ns; g.n_parts = np; g.rv = rv;
     const int base = atomicAdd(p.tc_counters, ns * np);
     for (int i = 0; i < ns * np; i++) p.tc_items[base + i] = make_int2(crop, (i % ns) | ((i / ns) << 16));
@@ -502,6 +517,7 @@ __device__ void tc_route(CropGeom& g, const PPParams& p, int crop) {
 // (L2-resident), so that the four slab CTAs of the main kernel only copy what they need.
 __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) {
     __shared__ CropGeom g;
+    __shared__ PlanScratch ps;
     const int crop = blockIdx.x, tid = threadIdx.x;
     const int out = p.out;
     if (tid == 0) {
@@ -520,6 +536,8 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
             g.off_y = o;
             if (g.regime == REG_GENERAL) o += g.oh + 2 * g.oh * tab_ycap(g);
             else if (g.regime == REG_LINEAR) o += 4 * g.oh;
+            o = (o + 3) & ~3;
+            g.off_tc = o; o += 8 * TC_MAX_STRIPS + 8 * 4;
             g.tab_ok = (o <= p.table_stride) ? 1 : 0;
         }
     }
@@ -535,6 +553,7 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
                 bicubic_coeffs(xx, g.rw, g.h_scale, g.h_fs, g.h_sup, g.h_ks, xm, n, h_kk + (size_t)xx * KSH);
                 for (int j = g.h_ks; j < KSH; j++) h_kk[(size_t)xx * KSH + j] = 0;
                 h_xmin[xx] = xm; h_n[xx] = n;
+                if (xx < PA_MAX_WINDOW) { ps.h_xmin[xx] = (short)xm; ps.h_n[xx] = (uint8_t)n; }
             }
         }
         if (g.vact) {
@@ -543,6 +562,7 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
                 int ym, n;
                 bicubic_coeffs(i, g.rh, g.v_scale, g.v_fs, g.v_sup, g.v_ks, ym, n, v_kk + (size_t)i * g.v_ks);
                 v_ymin[i] = ym; v_n[i] = n;
+                if (i < PA_MAX_WINDOW) { ps.v_ymin[i] = (short)ym; ps.v_n[i] = (uint8_t)n; }
             }
         }
         if (g.regime == REG_GENERAL) {
@@ -551,6 +571,7 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
             for (int dx = tid; dx < out; dx += 128) {
                 int n = area_entries(dx, sd, g.scale_x, xt_si + dx * xcap, xt_al + dx * xcap, xcap);
                 xt_n[dx] = n < xcap ? n : xcap;
+                if (dx < 128 && n >= 1) { ps.x_first[dx] = (short)xt_si[dx * xcap]; ps.x_last[dx] = (short)xt_si[dx * xcap + (n < xcap ? n : xcap) - 1]; }
             }
             int* yt_n = tab + g.off_y; int* yt_s = yt_n + g.oh; float* yt_b = (float*)(yt_s + g.oh * ycap);
             for (int i = tid; i < g.oh; i += 128) {
@@ -576,7 +597,7 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     __syncthreads();   // the tables written above are read back below (same block: visible after the barrier)
     if (tid == 0) {
         g.route = 0; g.n_strips = 0; g.n_parts = 0; g.rv = 0;
-        if (p.tc_enable && g.status == PA_CROP_OK && g.tab_ok) tc_route(g, p, crop);
+        if (p.tc_enable && g.status == PA_CROP_OK && g.tab_ok) tc_route(g, p, crop, ps);
     }
     __syncthreads();
     // publish the geometry (plain words; the main kernel launches after this one on the same stream)
