@@ -14,12 +14,12 @@ constexpr int CG_EPI_WARPS = 16;
 // resident beside them (at the natural 96 the conv CTA would have to wait for the staging kernel to drain).
 constexpr int CG_MAX_REGS = 88;
 constexpr int CG_THREADS = (CG_FIRST_EPI_WARP + CG_EPI_WARPS) * 32;  // TMA warp, MMA warp, 16 epilogue warps
-// Dynamic shared memory the conv kernels may plan with: 222 KB of the 228 KB per SM, so that a few 64-thread CTAs of
-// the window-staging kernel (1 KB of reserved shared memory each) can stay resident beside a conv CTA.
+// Dynamic shared memory the conv kernels may plan with: 220 KB of the 228 KB per SM, so that one CTA of the
+// window-staging kernel (a 5.5 KB TMA ring + 1 KB of reserved shared memory) can stay resident beside a conv CTA.
 inline size_t conv_smem_budget() {
     static size_t v = 0;
     if (!v) {
-        int kb = 222;
+        int kb = 220;
 #ifdef PA_EXPERIMENT
         const char* e = getenv("PA_CONV_SMEM_KB");
         if (e && atoi(e) >= 64 && atoi(e) <= 227) kb = atoi(e);

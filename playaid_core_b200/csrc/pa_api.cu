@@ -322,7 +322,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         rc = launch_preprocess(p, (cudaStream_t)stream);
     }
     if (rc != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess launch");
-    p.smem_bytes = 224 * 1024;
+    p.smem_bytes = 216 * 1024;   // not the whole carve-out: a window-staging worker (6.7 KB) may sit on the SM and must not block this launch
     p.first_pass_smem = cfg_smem_kb * 1024;
     p.defer_too_large = 0;
     {

@@ -1315,15 +1315,98 @@ __global__ void __maxnreg__(64) stage_windows_kernel(const StageParams p) {
   }
 }
 
+// Same job with the TMA unit: a worker is ONE thread that pulls 16-byte aligned row segments with cp.async.bulk
+// (pinned host -> shared memory ring, mbarrier completion) and pushes them on with cp.async.bulk (shared -> HBM).
+// Larger requests cross PCIe (48.9 GB/s against 46.4 for the 16-byte loads above, tools/micro/pcie_probe.cu), no data
+// passes through registers or L1, and a worker needs one thread and a 5.5 KB ring beside the compute CTAs.
+constexpr int SB_STAGES = 4, SB_LAG = 2, SB_PIECE = 1408;   // ring stages, stores in flight before a stage is reused, bytes per stage
+__global__ void __launch_bounds__(32) stage_windows_bulk_kernel(const StageParams p) {
+    __shared__ __align__(128) uint8_t ring[SB_STAGES * SB_PIECE];
+    __shared__ uint64_t full[SB_STAGES];
+    if (threadIdx.x != 0) return;
+    {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (!((int)smid < p.max_sm && atomicAdd(&p.sched[1 + (smid & 255)], 1) < ST_PER_SM)) return;
+    }
+    for (int i = 0; i < SB_STAGES; i++) mbar_init(&full[i], 1);
+    fence_barrier_init();
+    uint32_t uses = 0;      // pieces that have gone through the ring so far (stage = uses % SB_STAGES, parity from uses / SB_STAGES)
+    const int n_items = p.n_crops * ST_SPLIT;
+    for (;;) {
+        const int item = atomicAdd(&p.sched[0], 1);
+        if (item >= n_items) break;
+        const int crop = item / ST_SPLIT, part = item - crop * ST_SPLIT;
+        const int32_t* box = p.boxes + (int64_t)crop * PA_BOX_STRIDE;
+        const int frame = box[0] - p.frame_base;
+        const int cw = box[3], ch = box[4];
+        const int sd = cw > ch ? cw : ch;
+        if (frame < 0 || frame >= p.n_frames || sd < 0) continue;
+        int x0, y0, rw, rh;
+        crop_window(box[1], box[2], sd, p.H, p.W, p.padding, x0, y0, rw, rh);
+        if (rw <= 0 || rh <= 0) continue;
+        const int64_t fo = (int64_t)frame * p.fstride;
+        const int64_t row0 = (int64_t)y0 * p.pitch + (int64_t)x0 * 3;
+        const int shift = (int)(row0 & 15);
+        const int rowb = ((shift + rw * 3 + 15) >> 4) << 4;                 // 16-byte aligned cover of a window row
+        const int ppr = (rowb + SB_PIECE - 1) / SB_PIECE;                   // pieces per row
+        const int plen = (((rowb + ppr - 1) / ppr) + 15) & ~15;             // bytes per piece (the last one may be shorter)
+        const int r_begin = (int)((int64_t)part * rh / ST_SPLIT), r_end = (int)((int64_t)(part + 1) * rh / ST_SPLIT);
+        const int n_pieces = (r_end - r_begin) * ppr;
+        const int64_t base = fo + row0 - shift;
+        auto piece = [&](int j, int64_t& off, int& len) {
+            const int r = r_begin + j / ppr, q = j - (j / ppr) * ppr;
+            off = base + (int64_t)r * p.pitch + (int64_t)q * plen;
+            len = min(plen, rowb - q * plen);
+            if (off + len > p.frames_bytes) len = (int)max((p.frames_bytes - off) & ~(int64_t)15, (int64_t)0);   // tail of the last frame
+        };
+        auto load = [&](int j) {
+            int64_t off; int len;
+            piece(j, off, len);
+            const uint32_t st = (uses + (uint32_t)j) % SB_STAGES;
+            if (len > 0) {
+                mbar_arrive_expect_tx(&full[st], (uint32_t)len);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(ring + st * SB_PIECE)), "l"(p.src + off), "r"(len), "r"(smem_u32(&full[st])) : "memory");
+            } else {
+                mbar_arrive(&full[st]);      // nothing to fetch: complete the phase so the consumer's wait falls through
+            }
+        };
+        int issued = 0;
+        for (; issued < n_pieces && issued < SB_STAGES - SB_LAG; issued++) load(issued);
+        for (int j = 0; j < n_pieces; j++) {
+            const uint32_t u = uses + (uint32_t)j, st = u % SB_STAGES;
+            mbar_wait(&full[st], (u / SB_STAGES) & 1);
+            int64_t off; int len;
+            piece(j, off, len);
+            if (len > 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(p.dst + off), "r"(smem_u32(ring + st * SB_PIECE)), "r"(len) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(SB_LAG - 1) : "memory");   // the store SB_LAG pieces back has read its stage
+            if (issued < n_pieces) { load(issued); issued++; }
+            // bytes of the last frame's last rows that the aligned cover cannot fetch as a 16-byte multiple
+            const int want = min(plen, rowb - (j - (j / ppr) * ppr) * plen);
+            for (int k = len; k < want && off + k < p.frames_bytes; k++) p.dst[off + k] = p.src[off + k];
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        uses += (uint32_t)n_pieces;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream) {
     int grid = p.n_crops * ST_SPLIT;
     if (grid > ST_CTAS_PER_SM * num_sms) grid = ST_CTAS_PER_SM * num_sms;
     if (cudaMemsetAsync(p.sched, 0, PA_STAGE_SCHED_INTS * sizeof(int), stream) != cudaSuccess) return PA_ERR_CUDA;
     static int unroll = 0, threads = 0, max_sm = 0;
+    static bool use_ldst = false;
     if (!unroll) {
         const char* e;
         unroll = 8; threads = ST_THREADS; max_sm = 1 << 20;
+        cudaFuncSetAttribute(stage_windows_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #ifdef PA_EXPERIMENT
+        use_ldst = getenv("PA_ST_LDST") != nullptr;
         unroll = (e = getenv("PA_ST_UNROLL")) ? atoi(e) : 8;
         threads = (e = getenv("PA_ST_THREADS")) ? atoi(e) : ST_THREADS;
         max_sm = (e = getenv("PA_ST_SMS")) ? atoi(e) : 1 << 20;
@@ -1339,6 +1422,12 @@ int launch_stage_windows(const StageParams& p, int num_sms, cudaStream_t stream)
     }
     StageParams q = p;
     q.max_sm = max_sm;
+    // TMA bulk copies need 16-byte aligned rows on both sides; anything else takes the load/store kernel
+    const bool bulk_ok = ((p.pitch & 15) == 0) && ((p.fstride & 15) == 0) && (((uintptr_t)p.src & 15) == 0) && (((uintptr_t)p.dst & 15) == 0);
+    if (bulk_ok && !use_ldst) {
+        stage_windows_bulk_kernel<<<grid, 32, 0, stream>>>(q);
+        return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    }
     if (unroll == 2) stage_windows_kernel<2><<<grid, threads, 0, stream>>>(q);
     else if (unroll == 4) stage_windows_kernel<4><<<grid, threads, 0, stream>>>(q);
     else stage_windows_kernel<8><<<grid, threads, 0, stream>>>(q);
