@@ -68,6 +68,8 @@ __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps m
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (warp >= 2) pdl_wait();     // the epilogue writes an activation buffer an earlier kernel may still read
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
@@ -78,6 +80,7 @@ __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps m
                     for (int ky = 0; ky < 7; ky++) tma_load_2d(sB + pl * C1_B_PLANE + ky * C1_B_KY, &maps.b[pl], bfull, ky * 32, 0);
             }
             __syncwarp();
+            pdl_wait();      // the weights above are constants; the crops come from the preprocess kernel
             int st = 0; uint32_t ph = 0;
             for (int n = blockIdx.x; n < a.n_crops; n += gridDim.x)
             for (int t = 0; t < 32; t++) {   // a CTA walks the tiles of a crop in order (the fused max-pool needs it)
@@ -211,7 +214,7 @@ static int launch_c1(const Conv1Maps& maps, const Conv1Args& a, int num_sms, cud
     }
     int grid = a.n_crops;   // whole crops per CTA
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, C1_THREADS, smem, stream>>>(maps, a);
+    if (launch_pdl(kern, dim3(grid), dim3(C1_THREADS), smem, stream, maps, a) != cudaSuccess) return PA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

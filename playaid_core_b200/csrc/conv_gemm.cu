@@ -69,6 +69,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (warp != 1) pdl_wait();     // producer and epilogue warps touch the previous layer's tensors; the MMA warp only shared memory
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
@@ -184,7 +186,7 @@ static int launch_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cud
     }
     int grid = args.m_tiles * args.n_tiles;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, CG_THREADS, smem, stream>>>(maps, args);
+    if (launch_pdl(kern, dim3(grid), dim3(CG_THREADS), smem, stream, maps, args) != cudaSuccess) return PA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

@@ -56,6 +56,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     cluster_sync_all();            // both CTAs' barriers exist before anything is signalled across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (warp != 1) pdl_wait();     // producer and epilogue warps touch the previous layer's tensors; the MMA warp only shared memory
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -165,7 +167,7 @@ static int launch2_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cu
     const int pair_tiles = ((args.m_tiles + 1) / 2) * args.n_tiles;
     int clusters = num_sms / 2;
     if (clusters > pair_tiles) clusters = pair_tiles;
-    kern<<<2 * clusters, CG_THREADS, smem, stream>>>(maps, args);   // cluster shape comes from __cluster_dims__
+    if (launch_pdl(kern, dim3(2 * clusters), dim3(CG_THREADS), smem, stream, maps, args) != cudaSuccess) return PA_ERR_CUDA;   // cluster shape comes from __cluster_dims__
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

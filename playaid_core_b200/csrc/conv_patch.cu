@@ -58,6 +58,8 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (warp >= CG_FIRST_EPI_WARP) pdl_wait();   // epilogue warps read the residual / write the output of earlier layers' buffers
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====
@@ -69,6 +71,7 @@ conv_patch_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, co
                         tma_load_2d(wres + (size_t)(tap * kb + kc) * B_BYTES, &maps.b[0], wfull, tap * args.k_per_tap + kc * CG_BLOCK_K, 0);
             }
             __syncwarp();
+            pdl_wait();      // the resident weights above do not depend on the previous layer; the activation patches do
             int st = 0; uint32_t ph = 0;
             const int pix_per_img = args.ho * args.wo;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -201,7 +204,7 @@ static int launch_p(const ConvMaps& maps, const ConvArgs& args, const PatchGeom&
     }
     int grid = args.m_tiles * args.n_tiles;
     if (grid > num_sms) grid = num_sms;
-    kern<<<grid, CG_THREADS, smem, stream>>>(maps, args, pg);
+    if (launch_pdl(kern, dim3(grid), dim3(CG_THREADS), smem, stream, maps, args, pg) != cudaSuccess) return PA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

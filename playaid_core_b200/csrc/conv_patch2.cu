@@ -54,6 +54,8 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    if (warp >= CG_FIRST_EPI_WARP) pdl_wait();   // epilogue warps read the residual / write the output of earlier layers' buffers
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -66,6 +68,7 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
                                  (int)rank * HALF_N);
         }
         __syncwarp();
+        pdl_wait();      // the resident weights above do not depend on the previous layer; the activation patches do
         int st = 0; uint32_t ph = 0;
         const int pix_per_img = args.ho * args.wo;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
@@ -198,7 +201,7 @@ static int launch_p2(const ConvMaps& maps, const ConvArgs& args, const PatchGeom
     const int pair_tiles = (args.m_tiles + 1) / 2;
     int clusters = num_sms / 2;
     if (clusters > pair_tiles) clusters = pair_tiles;
-    kern<<<2 * clusters, CG_THREADS, smem, stream>>>(maps, args, pg);
+    if (launch_pdl(kern, dim3(2 * clusters), dim3(CG_THREADS), smem, stream, maps, args, pg) != cudaSuccess) return PA_ERR_CUDA;
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 

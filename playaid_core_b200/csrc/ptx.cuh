@@ -68,6 +68,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with launch_pdl() may start while its predecessor in the stream is still draining: everything before
+// pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, weight loads) overlaps the predecessor's tail; pdl_wait()
+// returns once the predecessor has completed and its writes are visible. pdl_launch_dependents() lets the successor's CTAs
+// be scheduled as soon as this grid's CTAs have all issued it (they then take the SMs this grid's CTAs leave).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(desc) : "memory");
@@ -245,6 +253,18 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     const uint16_t h0 = enc16<F16>(v0), h1 = enc16<F16>(v1);
     hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
     lo = (uint32_t)enc16<F16>(v0 - dec16<F16>(h0)) | ((uint32_t)enc16<F16>(v1 - dec16<F16>(h1)) << 16);
+}
+
+// Host: launch `kern` with programmatic stream serialization allowed (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 }  // namespace pa

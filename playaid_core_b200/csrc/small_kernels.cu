@@ -15,6 +15,8 @@ __global__ void avgpool_kernel(const bf16* __restrict__ in_hi, const bf16* __res
                                bf16* __restrict__ out_lo, int n, int hw, int c) {
     const int64_t total = (int64_t)n * c;
     const float inv = 1.f / (float)hw;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int ch = (int)(i % c);
         const int64_t b = i / c;
@@ -38,14 +40,16 @@ int launch_avgpool(const bf16* in_hi, const bf16* in_lo, bf16* out_hi, bf16* out
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (f16) avgpool_kernel<true><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
-    else avgpool_kernel<false><<<blocks, 256, 0, stream>>>(in_hi, in_lo, out_hi, out_lo, n, hw, c);
-    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    cudaError_t e = f16 ? launch_pdl(avgpool_kernel<true>, dim3(blocks), dim3(256), 0, stream, in_hi, in_lo, out_hi, out_lo, n, hw, c)
+                        : launch_pdl(avgpool_kernel<false>, dim3(blocks), dim3(256), 0, stream, in_hi, in_lo, out_hi, out_lo, n, hw, c);
+    return e == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------- fp32 -> bf16 hi (+ lo)
 template <bool F16>
 __global__ void split_kernel(const float* __restrict__ in, bf16* __restrict__ out_hi, bf16* __restrict__ out_lo, int64_t n) {
+    if (threadIdx.x == 0) pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float v = in[i];
         const uint16_t h = enc16<F16>(v);
@@ -58,9 +62,9 @@ int launch_split_f32(const float* in, bf16* out_hi, bf16* out_lo, int64_t n, int
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (f16) split_kernel<true><<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
-    else split_kernel<false><<<blocks, 256, 0, stream>>>(in, out_hi, out_lo, n);
-    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    cudaError_t e = f16 ? launch_pdl(split_kernel<true>, dim3(blocks), dim3(256), 0, stream, in, out_hi, out_lo, n)
+                        : launch_pdl(split_kernel<false>, dim3(blocks), dim3(256), 0, stream, in, out_hi, out_lo, n);
+    return e == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------- temporal head, one CTA (512 threads) per window
@@ -77,6 +81,8 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
     __shared__ int win_ok;
     const int w = blockIdx.x, t = threadIdx.x;
     const int pitch = a.seq * 512;
+    if (t == 0) pdl_launch_dependents();
+    pdl_wait();
     if (t == 0) {   // a window is only classified when every crop it reads exists (see pa_head)
         int ok = 1;
         if (a.feat_status)
@@ -149,8 +155,7 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
 
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
     if (a.n_actions > 128 || a.n_win <= 0) return PA_ERR_INVALID_ARG;
-    head_kernel<<<a.n_win, 512, 0, stream>>>(a);
-    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    return launch_pdl(head_kernel, dim3(a.n_win), dim3(512), 0, stream, a) == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 }  // namespace pa
