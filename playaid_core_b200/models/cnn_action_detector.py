@@ -82,6 +82,21 @@ class CNNActionDetector:
                 continue
             sd[k[6:] if k.startswith("model.") else k] = v.detach().to("cpu", torch.float32).contiguous()
         self.model._state = sd
+        # The two-product modes are fp32-exact only when the WEIGHTS are representable in the 16-bit operand format (the
+        # activations carry a second plane, the weights do not). A trained checkpoint is not: give the weights a residual
+        # plane too (three products per k-step) instead of silently rounding them.
+        if self.precision in ("f16x2", "bf16x2"):
+            dt = torch.float16 if self.half else torch.bfloat16
+            # "representable" up to 2^-20 of the tensor's largest weight: values below the format's normal range round
+            # with an absolute error (<= 2^-25 for half) that is far below fp32 noise; a trained fp32 tensor misses by 2^-12
+            inexact = [k for k, v in sd.items() if v.ndim >= 2 and
+                       float((v.to(dt).float() - v).abs().max()) > max(2.0 ** -20 * float(v.abs().max()), 2.0 ** -24)]
+            if inexact:
+                import warnings
+
+                self.precision = self.precision[:-1] + "3"
+                warnings.warn(f"{len(inexact)} weight tensors are not exactly representable in {dt}: using precision "
+                              f"'{self.precision}' (weights split as well) to keep fp32 parity", stacklevel=2)
         self._finalize()
         return self
 

@@ -395,3 +395,19 @@ def test_cfg5_dealt_matches_equal_single_pass(setup):
             assert torch.equal(gathered[r, o : o + lengths[m]], single[m]), (r, m)
             o += lengths[m]
     assert sorted(m for ids in parts for m in ids) == list(range(len(segs)))
+
+
+def test_unrounded_checkpoint_gets_three_products(setup):
+    """A checkpoint whose weights are not 16-bit representable (torchvision's default init here; any trained .ckpt) loaded
+    into the default two-product mode: the weights get a residual plane too (f16x3), with a warning, so that fp32 parity
+    does not silently depend on the weights' bit patterns."""
+    torch, _, _ = setup
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from workloads import weights
+
+    with pytest.warns(UserWarning, match="f16x3"):
+        m = CNNActionDetector(ACTIONS, sequence_length=7).eval().load_state_dict(weights.default_state_dict(0))
+    assert m.precision == "f16x3"
+    m2 = CNNActionDetector(ACTIONS, sequence_length=7).eval().load_state_dict(weights.calibrated_state_dict(0))
+    assert m2.precision == "f16x2"

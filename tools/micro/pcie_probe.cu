@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(32) pull_bulk(const uint8_t* src, uint8_t* dst
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-int main() {
+int main(int argc, char** argv) {
     const size_t bytes = (size_t)NF * FSTRIDE;
     uint8_t *h, *d;
-    if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { printf("host alloc failed\n"); return 1; }
+    const bool wc = argc > 1 && argv[1][0] == 'w';      // ./pcie_probe w : write-combined pinned memory
+    printf("pinned host memory: %s\n", wc ? "write-combined" : "default (cacheable)");
+    if (cudaHostAlloc(&h, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) { printf("host alloc failed\n"); return 1; }
     cudaMalloc(&d, bytes);
     for (size_t i = 0; i < bytes; i += 4096) h[i] = (uint8_t)(i >> 12);
     std::vector<Win> wins;
@@ -95,7 +97,7 @@ int main() {
     const double wbytes = (double)wins.size() * RH * SEG;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms;
-    for (int grid : {8, 16, 32, 74, 148, 592}) {
+    for (int grid : {32, 148}) {
         for (int rep = 0; rep < 2; rep++) {
             cudaEventRecord(e0);
             pull_ldst<<<grid, 32>>>(h, d, dw, (int)wins.size());
