@@ -74,6 +74,8 @@ extern "C" {
 
 #define PA_MAX_WINDOW 1920 /* widest raw window (pixels) the preprocess kernel stages */
 
+#define PA_LOG_STRIDE 10 /* doubles per ult_logger record handed to pa_boxes_from_log */
+
 typedef struct pa_ctx pa_ctx;
 typedef struct pa_model pa_model;
 
@@ -106,6 +108,19 @@ int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W
                   int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,
                   int swap_rb, const float* mean3_host, const float* std3_host, void* out, int out_dtype,
                   int out_layout, int32_t* status, void* stream);
+
+/*
+ * Fighter boxes on the device. Replaces, for n records at once, the bbox part of
+ * Fighter.set_from_json (playaid/fighter.py:487-539) with its camera math (calculate_intrinsic_matrix :66-84,
+ * calculate_lookat_matrix :87-120, project_point_to_pixel :123-155, np.round half-to-even) and
+ * YoloCrop.yolo_pixels' int() truncation (:305-314). fp64, bit-equal to the reference on its own records.
+ * log_records  double [n][PA_LOG_STRIDE] = {pos_x, pos_y, camera_position x y z, camera_target_position x y z,
+ *              focal length 1280 / (2 tan(fov / 2)) of the stage, frame index of the record}
+ * boxes        double [n][4] normalised (cx, cy, w, h) = Fighter.crop.yolo_crop(), or NULL
+ * crop_records int32 [n][PA_BOX_STRIDE] ready for pa_preprocess / pa_stage_windows, or NULL
+ */
+int pa_boxes_from_log(pa_ctx* ctx, const double* log_records, int n, int W, int H, double* boxes, int32_t* crop_records,
+                      void* stream);
 
 /*
  * Frames in PINNED HOST memory (what a decoder thread hands over): instead of copying whole frames to

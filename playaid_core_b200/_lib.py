@@ -14,10 +14,12 @@ DTYPE_U8, DTYPE_BF16, DTYPE_F32, DTYPE_BF16X2, DTYPE_F16, DTYPE_F16X2, DTYPE_BF1
 LAYOUT_NHWC, LAYOUT_NCHW, LAYOUT_NHWC4, LAYOUT_NHWC4P = 0, 1, 2, 3
 PREC_BF16, PREC_BF16X2, PREC_BF16X3, PREC_F16, PREC_F16X2, PREC_F16X3 = 0, 1, 2, 3, 4, 5
 BOX_STRIDE = 8
+LOG_STRIDE = 10
 
 # every symbol include/playaid_b200.h declares
 EXPORTS = [
     "pa_abi_version", "pa_status_string", "pa_last_error", "pa_ctx_create", "pa_ctx_destroy", "pa_preprocess", "pa_stage_windows",
+    "pa_boxes_from_log",
     "pa_model_create", "pa_model_destroy", "pa_model_set_tensor", "pa_model_finalize", "pa_model_precision",
     "pa_model_workspace_bytes", "pa_features", "pa_features_u8", "pa_crop_elems", "pa_head", "pa_launch_count", "pa_conv2d", "pa_stem",
     "pa_profile_begin", "pa_profile_end", "pa_resformer_create", "pa_resformer_finalize",
@@ -55,6 +57,7 @@ def load() -> ctypes.CDLL:
     lib.pa_preprocess.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, i32, i32, i32, i32,
                                   c.POINTER(c.c_float), c.POINTER(c.c_float), vp, i32, i32, vp, vp]
     lib.pa_stage_windows.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, i32, i32, i32, vp, vp]
+    lib.pa_boxes_from_log.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.pa_model_create.argtypes = [vp, i32, i32, c.POINTER(vp)]
     lib.pa_resformer_create.argtypes = [vp, i32, i32, c.POINTER(vp)]
     lib.pa_resformer_finalize.argtypes = [vp, i32]

@@ -40,7 +40,7 @@ class MatchStream:
     """
 
     def __init__(self, det: "ActionDetector", boxes: np.ndarray, H: int, W: int, frame_offset: int = 0,
-                 total_frames: int | None = None, own: tuple[int, int] | None = None):
+                 total_frames: int | None = None, own: tuple[int, int] | None = None, rec: torch.Tensor | None = None):
         self.det, self.H, self.W = det, int(H), int(W)
         self.N, self.F = int(boxes.shape[0]), int(boxes.shape[1])
         self.offset = int(frame_offset)
@@ -51,8 +51,10 @@ class MatchStream:
         self.boxes = boxes
         dev = det.model._device
         A, S = det.model.num_actions, det.num_frames_per_sample
-        rec = crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(self.N), self.F), self.W, self.H)
-        self.rec = torch.from_numpy(rec).to(dev)
+        if rec is None:     # host geometry -> crop records; `rec` = records already on the device (pa_boxes_from_log)
+            rec = torch.from_numpy(crop_records(boxes.reshape(-1, 4), np.repeat(np.arange(self.N), self.F), self.W, self.H)).to(dev)
+        assert rec.dtype == torch.int32 and tuple(rec.shape) == (self.N * self.F, _lib.BOX_STRIDE) and rec.is_cuda
+        self.rec = rec
         n_own = self.own[1] - self.own[0]
         self.feat = torch.zeros((self.N * self.F, 1000), dtype=torch.float32, device=dev)
         self.logp = torch.empty((n_own, self.F, A), dtype=torch.float32, device=dev)
@@ -233,6 +235,20 @@ class ActionDetector:
         """boxes float64 [N,F,4]: every (frame, fighter) box of the match (from the ult_logger log).
         `shard` = frame_offset / total_frames / own for one rank's slice (see parallel.frame_shard)."""
         return MatchStream(self, boxes, H, W, **shard)
+
+    def stream_from_log(self, timeline, H: int, W: int, **shard) -> MatchStream:
+        """`timeline` = `load_ground_truth_from_path(log)` records (per frame, per fighter). The box geometry runs on the
+        device (`pa_boxes_from_log`): only nine doubles per record cross PCIe, the crop records never
+        exist on the host. Fighters in `fighter_id` order like `update_fighters_from_timeline` (timeline.py:186-201)."""
+        from .fighter import boxes_from_records_device, log_record_array
+
+        n_f = len(timeline[0]) if timeline else 0
+        flat = [r for frame in timeline for r in sorted(frame, key=lambda x: x["fighter_id"])]
+        if any("crop" in r for r in flat):    # AI crop overrides (fighter.py:503-504) take the host path
+            return self.stream(boxes_from_timeline(timeline), H, W, **shard)
+        arr = log_record_array(flat, np.repeat(np.arange(len(timeline)), n_f))
+        boxes_d, rec_d = boxes_from_records_device(arr, W, H, self.model._device)
+        return MatchStream(self, boxes_d.cpu().numpy().reshape(len(timeline), n_f, 4), H, W, rec=rec_d, **shard)
 
     def classify_clip(self, frames: torch.Tensor, boxes: np.ndarray, chunk: int = 256) -> dict:
         """frames uint8 CUDA [N,H,W,3] (BGR, as decoded by cv2), boxes float64 [N,F,4] normalised.

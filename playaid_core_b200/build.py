@@ -21,7 +21,7 @@ SOURCES = {
     "conv_patch.cu": [],
     "conv_patch2.cu": [],
     "conv1.cu": [],
-    "small_kernels.cu": [],
+    "small_kernels.cu": ["-fmad=false"],   # the fp64 box geometry must not be contracted (bit-equal to numpy); the other kernels here are memory-bound
     "transformer_kernels.cu": [],
     "pa_api.cu": [],
 }

@@ -334,6 +334,14 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     return PA_OK;
 }
 
+extern "C" int pa_boxes_from_log(pa_ctx* ctx, const double* log_records, int n, int W, int H, double* boxes, int32_t* crop_records, void* stream) {
+    if (!ctx || !log_records || n < 0 || W <= 0 || H <= 0 || (!boxes && !crop_records)) return PA_ERR_INVALID_ARG;
+    ProfSpan sp(ctx, "boxes_from_log", (cudaStream_t)stream);
+    if (launch_boxes(log_records, n, W, H, boxes, crop_records, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "boxes launch");
+    ctx->launches += 1;
+    return PA_OK;
+}
+
 extern "C" size_t pa_crop_elems(int out_size) { return (size_t)out_size * (out_size + 8) * 4; }
 
 // ------------------------------------------------------------------------------------------------ model

@@ -157,6 +157,7 @@ struct HeadArgs {
     float* conf;           // [n_win]
 };
 int launch_head(const HeadArgs& a, cudaStream_t stream);
+int launch_boxes(const double* rec, int n, int W, int H, double* boxes, int32_t* crops, cudaStream_t stream);
 
 // ---------------------------------------------------------------- ResFormer encoder pieces (transformer_kernels.cu)
 int launch_tokens(const float* ffn, const float* enc, float* x, int T, int S, int hidden, cudaStream_t stream);

@@ -153,6 +153,68 @@ __global__ void __launch_bounds__(512) head_kernel(const HeadArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- fighter boxes from ult_logger records
+// Reference playaid/fighter.py:487-539 (Fighter.set_from_json, bbox part) with its camera math :66-155: look-at pose
+// from camera / target, the four world-space corners around the fighter projected through the pose's inverse and the
+// pin-hole intrinsics of a virtual 1280 x 720 image, np.round (half to even), centre / extent of the rounded pixels,
+// then YoloCrop.yolo_pixels' int() truncation (:305-314). fp64 throughout, no FMA contraction (the file is compiled
+// with -fmad=false), IEEE sqrt / division: the rounded pixels -- hence the boxes -- equal the host path's.
+// rec: [n][PA_LOG_STRIDE] doubles {pos_x, pos_y, cam x y z, target x y z, focal length, frame index}
+__global__ void boxes_kernel(const double* __restrict__ rec, int n, int W, int H, double* __restrict__ boxes, int32_t* __restrict__ crops) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = rec + (size_t)i * PA_LOG_STRIDE;
+    const double px_ = r[0], py_ = r[1];
+    const double c[3] = {r[2], r[3], r[4]}, t[3] = {r[5], r[6], r[7]};
+    const double f = r[8];
+    // calculate_lookat_matrix: forward = normalize(cam - target); right = normalize(cross(up, forward)); up = cross(forward, right)
+    double fw[3] = {c[0] - t[0], c[1] - t[1], c[2] - t[2]};
+    double nrm = sqrt((fw[0] * fw[0] + fw[1] * fw[1]) + fw[2] * fw[2]);
+    fw[0] /= nrm; fw[1] /= nrm; fw[2] /= nrm;
+    double rt[3] = {1.0 * fw[2] - 0.0 * fw[1], 0.0 * fw[0] - 0.0 * fw[2], 0.0 * fw[1] - 1.0 * fw[0]};
+    nrm = sqrt((rt[0] * rt[0] + rt[1] * rt[1]) + rt[2] * rt[2]);
+    rt[0] /= nrm; rt[1] /= nrm; rt[2] /= nrm;
+    const double up[3] = {fw[1] * rt[2] - fw[2] * rt[1], fw[2] * rt[0] - fw[0] * rt[2], fw[0] * rt[1] - fw[1] * rt[0]};
+    // pose M = [R | cam] with rows right / up / -forward; its inverse = [R^-1 | -R^-1 cam], R^-1 by cofactors
+    const double R[3][3] = {{rt[0], rt[1], rt[2]}, {up[0], up[1], up[2]}, {-fw[0], -fw[1], -fw[2]}};
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    double Ri[3][3];
+    Ri[0][0] = (R[1][1] * R[2][2] - R[1][2] * R[2][1]) / det; Ri[0][1] = (R[0][2] * R[2][1] - R[0][1] * R[2][2]) / det; Ri[0][2] = (R[0][1] * R[1][2] - R[0][2] * R[1][1]) / det;
+    Ri[1][0] = (R[1][2] * R[2][0] - R[1][0] * R[2][2]) / det; Ri[1][1] = (R[0][0] * R[2][2] - R[0][2] * R[2][0]) / det; Ri[1][2] = (R[0][2] * R[1][0] - R[0][0] * R[1][2]) / det;
+    Ri[2][0] = (R[1][0] * R[2][1] - R[1][1] * R[2][0]) / det; Ri[2][1] = (R[0][1] * R[2][0] - R[0][0] * R[2][1]) / det; Ri[2][2] = (R[0][0] * R[1][1] - R[0][1] * R[1][0]) / det;
+    double ti[3];
+    for (int a = 0; a < 3; a++) ti[a] = -((Ri[a][0] * c[0] + Ri[a][1] * c[1]) + Ri[a][2] * c[2]);
+    const double ox[4] = {-10.0, 10.0, -10.0, 10.0}, oy[4] = {20.0, 20.0, -3.0, -3.0};
+    long long xs[4], ys[4];
+    for (int k = 0; k < 4; k++) {
+        const double w[3] = {px_ + ox[k], py_ + oy[k], 0.0};
+        double pc[3];
+        for (int a = 0; a < 3; a++) pc[a] = ((Ri[a][0] * w[0] + Ri[a][1] * w[1]) + Ri[a][2] * w[2]) + ti[a];
+        const double nx = pc[0] / pc[2], ny = pc[1] / pc[2];
+        const double u = f * nx + 640.0, v = 720.0 - (f * ny + 360.0);      // K @ normalised point, y flipped
+        xs[k] = (long long)rint(u); ys[k] = (long long)rint(v);           // np.round: half to even
+    }
+    const long long sx = xs[0] + xs[1] + xs[2] + xs[3], sy = ys[0] + ys[1] + ys[2] + ys[3];
+    const long long wx = max(max(xs[0], xs[1]), max(xs[2], xs[3])) - min(min(xs[0], xs[1]), min(xs[2], xs[3]));
+    const long long wy = max(max(ys[0], ys[1]), max(ys[2], ys[3])) - min(min(ys[0], ys[1]), min(ys[2], ys[3]));
+    const double b[4] = {(double)sx / 4.0 / 1280.0, (double)sy / 4.0 / 720.0, (double)wx / 1280.0, (double)wy / 720.0};
+    if (boxes) for (int a = 0; a < 4; a++) boxes[(size_t)i * 4 + a] = b[a];
+    if (crops) {
+        int32_t* o = crops + (size_t)i * PA_BOX_STRIDE;
+        o[0] = (int32_t)r[9];
+        o[1] = (int32_t)(b[0] * (double)W); o[2] = (int32_t)(b[1] * (double)H);     // int(): truncation toward zero
+        o[3] = (int32_t)(b[2] * (double)W); o[4] = (int32_t)(b[3] * (double)H);
+        o[5] = o[6] = o[7] = 0;
+    }
+}
+
+int launch_boxes(const double* rec, int n, int W, int H, double* boxes, int32_t* crops, cudaStream_t stream) {
+    if (n <= 0) return PA_OK;
+    boxes_kernel<<<(n + 127) / 128, 128, 0, stream>>>(rec, n, W, H, boxes, crops);
+    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+}
+
 int launch_head(const HeadArgs& a, cudaStream_t stream) {
     if (a.n_actions > 128 || a.n_win <= 0) return PA_ERR_INVALID_ARG;
     return launch_pdl(head_kernel, dim3(a.n_win), dim3(512), 0, stream, a) == cudaSuccess ? PA_OK : PA_ERR_CUDA;

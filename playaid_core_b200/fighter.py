@@ -96,6 +96,47 @@ def boxes_from_records(records) -> np.ndarray:
     return out
 
 
+def log_record_array(records, frame_index=None) -> np.ndarray:
+    """Flat list of ult_logger dicts -> float64 [n, 10] rows {pos_x, pos_y, camera xyz, target xyz, focal length, frame}:
+    the input of `boxes_from_records_device` / `pa_boxes_from_log`. The focal length of the record's stage is taken here
+    (calculate_focal_length, reference fighter.py:31-48) so that the device uses the very double numpy computes."""
+    n = len(records)
+    a = np.empty((n, 10), dtype=np.float64)
+    if n == 0:
+        return a
+    a[:, 0] = [r["pos_x"] for r in records]
+    a[:, 1] = [r["pos_y"] for r in records]
+    a[:, 2:5] = [list(r["camera_position"].values()) for r in records]
+    a[:, 5:8] = [list(r["camera_target_position"].values()) for r in records]
+    fov = np.array([stage_fov(r["stage_id"]) for r in records], dtype=np.float64)
+    a[:, 8] = VIRTUAL_W / (2 * np.tan(np.deg2rad(fov) / 2))
+    a[:, 9] = np.arange(n) if frame_index is None else np.asarray(frame_index, dtype=np.float64)
+    return a
+
+
+def boxes_from_records_device(log_array, image_width: int, image_height: int, device=None):
+    """Device form of `boxes_from_records` + `crop_records`: float64 [n,10] rows from `log_record_array`
+    -> (boxes float64 CUDA [n,4], crop records int32 CUDA [n,8]); `pa_boxes_from_log`, one thread per record. Records that
+    carry an AI "crop" override are not handled here (use `boxes_from_records`)."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ctx = _lib.Context.get(dev)
+    rec = torch.as_tensor(np.ascontiguousarray(log_array, dtype=np.float64)).to(dev)
+    n = int(rec.shape[0])
+    boxes = torch.empty((n, 4), dtype=torch.float64, device=dev)
+    crops = torch.empty((n, _lib.BOX_STRIDE), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = ctx.lib.pa_boxes_from_log(ctx.handle, rec.data_ptr(), n, int(image_width), int(image_height), boxes.data_ptr(),
+                                       crops.data_ptr(), _lib.current_stream_ptr(dev))
+    _lib.check(rc, ctx.handle, "pa_boxes_from_log")
+    return boxes, crops
+
+
 def boxes_from_timeline(timeline) -> np.ndarray:
     """`load_ground_truth_from_path` output -> float64 [n_frames, n_fighters, 4]; fighters in
     `fighter_id` order like `update_fighters_from_timeline` (reference timeline.py:186-201)."""

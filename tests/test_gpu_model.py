@@ -411,3 +411,26 @@ def test_unrounded_checkpoint_gets_three_products(setup):
     assert m.precision == "f16x3"
     m2 = CNNActionDetector(ACTIONS, sequence_length=7).eval().load_state_dict(weights.calibrated_state_dict(0))
     assert m2.precision == "f16x2"
+
+
+def test_stream_from_log_uses_device_geometry(setup):
+    """`ActionDetector.stream_from_log` (box geometry + crop records on the device, pa_boxes_from_log) gives the labels of
+    the host-geometry stream bit for bit."""
+    torch, sd, _ = setup
+    from playaid_core_b200.action_detector import ActionDetector
+    from playaid_core_b200.anim_ontology import ACTIONS
+    from playaid_core_b200.fighter import boxes_from_records, yolo_pixels_batch
+    from playaid_core_b200.models.cnn_action_detector import CNNActionDetector
+    from workloads import synthetic
+
+    N = 60
+    recs = synthetic.synth_log_records(N, 2, seed=13)
+    boxes = boxes_from_records([r for f in recs for r in f]).reshape(N, 2, 4)
+    frames = synthetic.synth_frames(np.arange(N), yolo_pixels_batch(boxes, 1920, 1080), device="cuda")
+    det = ActionDetector(CNNActionDetector(ACTIONS, sequence_length=7).eval().load_state_dict(sd))
+    a = det.stream(boxes, 1080, 1920)
+    b = det.stream_from_log(recs, 1080, 1920)
+    assert torch.equal(a.rec, b.rec) and np.array_equal(a.boxes, b.boxes)
+    for st in (a, b):
+        st.push(frames)
+    assert torch.equal(a.label, b.label) and torch.equal(a.logp, b.logp)

@@ -306,3 +306,30 @@ def test_unaligned_frame_geometry(torch_cuda):
     assert not bad, bad[:10]
     assert np.array_equal(status_v.cpu().numpy(), status) and np.array_equal(out_v.cpu().numpy(), out)
     assert np.array_equal(status_s.cpu().numpy(), status) and np.array_equal(out_s.cpu().numpy(), out)
+
+
+def test_device_boxes_bit_equal_to_reference_and_host(torch_cuda, golden_dir):
+    """`pa_boxes_from_log` (fp64 camera geometry + np.round + int() truncation on the device) against
+    the 601 boxes recorded from the reference's Fighter(...).crop (tests/golden/bbox.npz) and against the vectorised host
+    path on 60 000 synthetic ult_logger records: boxes bit-equal, crop records identical."""
+    import json
+
+    from playaid_core_b200.fighter import boxes_from_records, boxes_from_records_device, log_record_array, yolo_pixels_batch
+    from workloads import synthetic
+
+    g = np.load(os.path.join(golden_dir, "bbox.npz"))
+    recs = json.loads(str(g["records"]))
+    boxes, crops = boxes_from_records_device(log_record_array(recs), 1920, 1080)
+    assert np.array_equal(boxes.cpu().numpy(), g["boxes"])
+    assert np.array_equal(crops.cpu().numpy()[:, 1:5], g["yolo_pixels"])
+    assert np.array_equal(crops.cpu().numpy()[:, 0], np.arange(len(recs)))
+    n = 30000
+    log = synthetic.synth_log_records(n, 2, seed=77, stage_id=95)      # fov 30 stage
+    log += synthetic.synth_log_records(n // 2, 2, seed=78, stage_id=0, pos_x_range=(-80.0, 80.0), pos_y_range=(0.0, 60.0))
+    flat = [r for f in log for r in f]
+    want = boxes_from_records(flat)
+    frame_idx = np.repeat(np.arange(len(log)), 2)
+    got, rec = boxes_from_records_device(log_record_array(flat, frame_idx), 1920, 1080)
+    assert np.array_equal(got.cpu().numpy(), want)
+    rec = rec.cpu().numpy()
+    assert np.array_equal(rec[:, 1:5], yolo_pixels_batch(want, 1920, 1080)) and np.array_equal(rec[:, 0], frame_idx) and not rec[:, 5:].any()
