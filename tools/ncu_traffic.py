@@ -30,7 +30,7 @@ def agg(pred):
     return {"launches": len(sel), "dram_bytes": sum(l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0) for l in sel),
             "time_us": sum(l.get("gpu__time_duration.sum", 0) for l in sel)}
 out = {"source": sys.argv[1], "step_index": 2, "kernels_in_step": len(step),
-       "conv": agg(lambda n: "conv" in n), "preprocess": agg(lambda n: n.startswith("pa::preprocess_kernel") or "preprocess_kernel(" in n),
+       "conv": agg(lambda n: "conv" in n), "preprocess": agg(lambda n: "preprocess_kernel(" in n or "preprocess_tc_kernel(" in n),
        "all": agg(lambda n: True),
        "per_kernel": [{"name": l["name"][:60], "dram_bytes": l.get("dram__bytes_read.sum", 0) + l.get("dram__bytes_write.sum", 0),
                        "time_us": l.get("gpu__time_duration.sum", 0)} for l in step]}
