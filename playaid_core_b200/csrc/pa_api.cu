@@ -185,8 +185,8 @@ static int get_scratch(pa_ctx* ctx, cudaStream_t st, int n_crops, pa_ctx::Scratc
     std::lock_guard<std::mutex> lock(ctx->scratch_mu);
     pa_ctx::Scratch& sc = ctx->scratch[st];
     if (!sc.stage_sched) PA_CUDA(ctx, cudaMalloc((void**)&sc.stage_sched, PA_STAGE_SCHED_INTS * sizeof(int)));
-    if (!sc.pp_deferred) PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_deferred, sizeof(int)));
-    if (!sc.tc_counters) PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_counters, 4 * sizeof(int)));
+    if (!sc.pp_deferred) { PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_deferred, sizeof(int))); PA_CUDA(ctx, cudaMemset(sc.pp_deferred, 0, sizeof(int))); }
+    if (!sc.tc_counters) { PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_counters, 4 * sizeof(int))); PA_CUDA(ctx, cudaMemset(sc.tc_counters, 0, 4 * sizeof(int))); }
     if (sc.cap < n_crops) {
         if (sc.pp_status) cudaFree(sc.pp_status);
         if (sc.pp_plan) cudaFree(sc.pp_plan);
@@ -258,8 +258,10 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     p.status = status;
     // pass 1: 108 KB of shared memory per 384-thread CTA (2 CTAs / SM) covers the usual fighter windows;
     // pass 2: the few crops that did not fit are redone with the whole carve-out (1 CTA / SM).
-    PA_CUDA(ctx, cudaMemsetAsync(status, 0x7f, (size_t)n_crops * sizeof(int32_t), (cudaStream_t)stream));
-    PA_CUDA(ctx, cudaMemsetAsync(sc->pp_deferred, 0, sizeof(int), (cudaStream_t)stream));
+    // No memsets in front of the plan kernel: it initialises the per-crop status and the deferred-slab counter itself, and the
+    // tensor-core kernel's last CTA re-zeroes the work-item counters. The plan kernel is launched with programmatic stream
+    // serialization and never waits on its predecessor (it reads only the crop records), so it runs under the tail of
+    // whatever kernel precedes it in the stream.
     p.deferred = sc->pp_deferred;
     // geometry + coefficient tables once per crop (L2-resident scratch of this stream)
     const size_t geom_b = preprocess_geom_bytes();
@@ -286,7 +288,6 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
             cudaGetLastError();   // a plain host pointer makes cudaPointerGetAttributes fail on old drivers: not an error here
         }
     }
-    PA_CUDA(ctx, cudaMemsetAsync(sc->tc_counters, 0, 4 * sizeof(int), (cudaStream_t)stream));
     {
         ProfSpan sp(ctx, "preprocess_plan", (cudaStream_t)stream);
         if (launch_preprocess_plan(p, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "preprocess plan launch");
@@ -316,6 +317,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     p.smem_bytes = cfg_smem_kb * 1024;
     p.first_pass_smem = 0;
     p.defer_too_large = 1;
+    p.overlap_prev = p.tc_enable;
     int rc;
     {
         ProfSpan sp(ctx, "preprocess", (cudaStream_t)stream);
@@ -325,6 +327,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     p.smem_bytes = 216 * 1024;   // not the whole carve-out: a window-staging worker (6.7 KB) may sit on the SM and must not block this launch
     p.first_pass_smem = cfg_smem_kb * 1024;
     p.defer_too_large = 0;
+    p.overlap_prev = 0;
     {
         ProfSpan sp(ctx, "preprocess_large_windows", (cudaStream_t)stream);
         rc = launch_preprocess(p, (cudaStream_t)stream);

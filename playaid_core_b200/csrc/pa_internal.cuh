@@ -29,6 +29,7 @@ struct PPParams {
     int smem_bytes;
     int first_pass_smem;  // > 0 in the second pass: skip slabs that fit in this many bytes
     int defer_too_large;  // first pass: leave slabs that do not fit to the second pass
+    int overlap_prev;     // first pass: the kernel in front of it is the tensor-core kernel (disjoint crops): launch without waiting for it
     int* deferred;        // device counter of slabs the first pass left for the second
     uint8_t* geoms;       // per-crop geometry written by preprocess_plan_kernel (or nullptr)
     int* tables;          // per-crop coefficient tables, table_stride int32 per crop (or nullptr)

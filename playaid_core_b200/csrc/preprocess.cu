@@ -520,7 +520,10 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     __shared__ PlanScratch ps;
     const int crop = blockIdx.x, tid = threadIdx.x;
     const int out = p.out;
+    if (tid == 0) pdl_launch_dependents();
     if (tid == 0) {
+        if (p.status) p.status[crop] = 0x7f7f7f7f;     // "not computed yet": every kernel that finishes a crop atomicMin's its outcome in
+        if (crop == 0) *p.deferred = 0;
         compute_geom(g, p.boxes + (int64_t)crop * PA_BOX_STRIDE, p.H, p.W, p.n_frames, out, p.padding);
         g.tab_ok = 0; g.off_h = g.off_v = g.off_x = g.off_y = 0;
         if (g.status == PA_CROP_OK) {
@@ -1209,13 +1212,18 @@ int launch_preprocess(const PPParams& p, cudaStream_t stream) {
         cudaFuncSetAttribute(preprocess_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
+    // Programmatic stream serialization, and the kernel never waits: its inputs (geometry, tables) come from the plan
+    // kernel, which is complete before the tensor-core kernel in front of it starts, and it touches only crops that kernel
+    // does not. Its CTAs (usually with nothing to do) drain through the SMs the tensor-core kernel's tail leaves free.
+    // The large-window pass needs the first pass's counter and is launched the ordinary way.
+    if (p.first_pass_smem == 0 && p.overlap_prev)
+        return launch_pdl(preprocess_kernel, dim3(p.n_crops * PP_SPLIT), dim3(p.threads), (size_t)p.smem_bytes, stream, p) == cudaSuccess ? PA_OK : PA_ERR_CUDA;
     preprocess_kernel<<<p.n_crops * PP_SPLIT, p.threads, p.smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
 int launch_preprocess_plan(const PPParams& p, cudaStream_t stream) {
-    preprocess_plan_kernel<<<p.n_crops, 128, 0, stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
+    return launch_pdl(preprocess_plan_kernel, dim3(p.n_crops), dim3(128), 0, stream, p) == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 size_t preprocess_geom_bytes() { return sizeof(CropGeom); }
 
