@@ -23,7 +23,12 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr int B_BYTES = HALF_N * CG_BLOCK_K * 2;
-    constexpr int STAGE_BYTES = NA * CG_A_BYTES + B_BYTES;
+    // Split precision (NA == 2) runs the K loop TWICE per tile: first every A_lo x B product, then every A_hi x B product,
+    // into the same accumulator. tcgen05 truncates the fp32 accumulator at every k-step (a bias of -0.5 ulp of the running
+    // sum per step, tests/test_gpu_layers.py::test_fp32_accumulation_floor_grows_with_k); interleaving hi and lo doubled
+    // the number of truncating steps on the full-size sum, whereas the lo pass alone sums to ~2^-11 of it (its ulp, and
+    // bias, are negligible). A stage holds ONE activation plane + the weight half-tile, so the weights stream twice.
+    constexpr int STAGE_BYTES = CG_A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
     const int S = args.num_stages;
     uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
@@ -69,6 +74,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             const int m0 = mt * CG_BLOCK_M;
             const int n0 = m0 / pix_per_img;
             const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
+            for (int pass = NA - 1; pass >= 0; pass--)      // plane 1 (lo) first, then plane 0 (hi)
             for (int tap = 0; tap < taps; tap++) {
                 const int ky = tap / args.taps_w, kx = tap - ky * args.taps_w;
                 int cx, cy, q = 0;
@@ -83,13 +89,11 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                 for (int kc = 0; kc < args.kb_per_tap; kc++) {
                     mbar_wait(&empty[st], ph ^ 1);
                     uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
-                    uint8_t* sb = sa + NA * CG_A_BYTES;
+                    uint8_t* sb = sa + CG_A_BYTES;
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * STAGE_BYTES);
                         const uint32_t lead_full = mapa_u32(&full[st], 0);
-#pragma unroll
-                        for (int pl = 0; pl < NA; pl++)
-                            tma2_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], lead_full, kc * CG_BLOCK_K, cx, cy, n0);
+                        tma2_load_4d(sa, &maps.a[pass][q], lead_full, kc * CG_BLOCK_K, cx, cy, n0);
                         tma2_load_2d(sb, &maps.b[1], lead_full, tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N + (int)rank * HALF_N);
                     }
                     __syncwarp();
@@ -109,19 +113,15 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; kb++) {
+                for (int kb = 0; kb < NA * num_kb; kb++) {      // NA passes over K (lo plane, then hi plane) into one accumulator
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-                    const uint32_t sb = sa + NA * CG_A_BYTES;
+                    const uint32_t sb = sa + CG_A_BYTES;
                     if (elect_one()) {
                         const uint64_t da0 = umma_desc_sw128(sa), db0 = umma_desc_sw128(sb);
-                        const uint64_t dal0 = (NA == 2) ? umma_desc_sw128(sa + CG_A_BYTES) : 0;
 #pragma unroll
-                        for (int k = 0; k < CG_BLOCK_K / 16; k++) {
-                            umma2_f16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
-                            if (NA == 2) umma2_f16(d_tmem, dal0 + 2 * k, db0 + 2 * k, idesc, 1);
-                        }
+                        for (int k = 0; k < CG_BLOCK_K / 16; k++) umma2_f16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
                         umma2_commit_multicast(&empty[st]);
                     }
                     __syncwarp();
@@ -148,7 +148,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 }
 
 int conv_gemm2_pick_stages(int block_n, int n_a) {
-    const size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)(block_n / 2) * CG_BLOCK_K * 2;
+    (void)n_a;      // a stage holds one activation plane: split precision makes two passes over K instead of doubling the stage
+    const size_t stage = (size_t)CG_A_BYTES + (size_t)(block_n / 2) * CG_BLOCK_K * 2;
     int s = (int)((PA_CONV_SMEM_BUDGET - 1024 - 256) / stage);
     return s > 8 ? 8 : s;
 }
@@ -156,7 +157,7 @@ int conv_gemm2_pick_stages(int block_n, int n_a) {
 template <int BLOCK_N, int NA>
 static int launch2_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cudaStream_t stream) {
     auto kern = conv_gemm2_kernel<BLOCK_N, NA>;
-    const size_t stage = (size_t)NA * CG_A_BYTES + (size_t)(BLOCK_N / 2) * CG_BLOCK_K * 2;
+    const size_t stage = (size_t)CG_A_BYTES + (size_t)(BLOCK_N / 2) * CG_BLOCK_K * 2;
     const size_t smem = 1024 + stage * args.num_stages + 256;
     static bool attr_set = false;
     if (!attr_set) {
