@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplayaid_b200.so")
+# PLAYAID_B200_LIB points at another build of the same library (A/B measurements); the default is the in-tree build
+LIB_PATH = os.environ.get("PLAYAID_B200_LIB") or os.path.join(_HERE, "libplayaid_b200.so")
 
 PA_OK = 0
 CROP_OK, CROP_INVALID, CROP_ZERO_DIV, CROP_TOO_LARGE = 1, 0, -2, -7

@@ -22,12 +22,18 @@
 
 namespace pa {
 
+// Split precisions make NA + NB - 1 PASSES over K per tile into one accumulator, smallest products first
+// (A_lo x B, A x B_lo, then A_hi x B_hi): the tensor core truncates the fp32 accumulator at every k-step, and a pass of
+// residual products sums to ~2^-11 of the result, so only the last pass truncates at full scale (see conv_gemm2.cu and
+// tests/test_gpu_layers.py::test_fp32_accumulation_floor_grows_with_k). A stage holds one A plane and one B plane.
 size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages) {
-    size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
+    (void)n_a; (void)n_b;
+    size_t stage = (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2;
     return 1024 /*alignment slack*/ + stage * num_stages + 256 /*barriers*/;
 }
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
-    size_t stage = (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
+    (void)n_a; (void)n_b;
+    size_t stage = (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2;
     int s = (int)((PA_CONV_SMEM_BUDGET - 1024 - 256) / stage);
     if (s > 8) s = 8;
     return s;
@@ -39,7 +45,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int B_BYTES = BLOCK_N * CG_BLOCK_K * 2;
-    constexpr int STAGE_BYTES = NA * CG_A_BYTES + NB * B_BYTES;
+    constexpr int STAGE_BYTES = CG_A_BYTES + B_BYTES;
+    constexpr int NPASS = NA + NB - 1;      // pass p: p < NA - 1 -> (A_lo, B_hi); p < NPASS - 1 -> (A_hi, B_lo); last -> (A_hi, B_hi)
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     const int S = args.num_stages;
     uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
@@ -82,6 +89,8 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                 const int m0 = mt * CG_BLOCK_M;
                 const int n0 = m0 / pix_per_img;
                 const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
+                for (int pass = 0; pass < NPASS; pass++) {
+                const int pla = (pass < NA - 1) ? 1 : 0, plb = (pass >= NA - 1 && pass < NPASS - 1) ? 1 : 0;
                 for (int tap = 0; tap < taps; tap++) {
                     const int ky = tap / args.taps_w, kx = tap - ky * args.taps_w;
                     int cx, cy, q = 0;
@@ -96,21 +105,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                     for (int kc = 0; kc < args.kb_per_tap; kc++) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
-                        uint8_t* sb = sa + NA * CG_A_BYTES;
+                        uint8_t* sb = sa + CG_A_BYTES;
                         if (args.debug & 2) {   // experiment: no operand loads at all (pure MMA issue rate)
                             if (elect_one()) mbar_arrive(&full[st]);
                         } else if (elect_one()) {
                             mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
-#pragma unroll
-                            for (int pl = 0; pl < NA; pl++)
-                                tma_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
-#pragma unroll
-                            for (int pl = 0; pl < NB; pl++)
-                                tma_load_2d(sb + pl * B_BYTES, &maps.b[pl], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                            tma_load_4d(sa, &maps.a[pla][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
+                            tma_load_2d(sb, &maps.b[plb], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
                         }
                         __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
                     }
+                }
                 }
             }
         }
@@ -126,22 +132,16 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < num_kb; kb++) {
+                for (int kb = 0; kb < NPASS * num_kb; kb++) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-                    const uint32_t sb = sa + NA * CG_A_BYTES;
+                    const uint32_t sb = sa + CG_A_BYTES;
                     if (elect_one()) {
                         // descriptors differ only in the 14-bit start-address field: add 32 B >> 4 per k-step
                         const uint64_t da0 = umma_desc_sw128(sa), db0 = umma_desc_sw128(sb);
-                        const uint64_t dal0 = (NA == 2) ? umma_desc_sw128(sa + CG_A_BYTES) : 0;
-                        const uint64_t dbl0 = (NB == 2) ? umma_desc_sw128(sb + B_BYTES) : 0;
 #pragma unroll
-                        for (int k = 0; k < CG_BLOCK_K / 16; k++) {
-                            umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
-                            if (NA == 2) umma_bf16(d_tmem, dal0 + 2 * k, db0 + 2 * k, idesc, 1);
-                            if (NB == 2) umma_bf16(d_tmem, da0 + 2 * k, dbl0 + 2 * k, idesc, 1);
-                        }
+                        for (int k = 0; k < CG_BLOCK_K / 16; k++) umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
                         umma_commit(&empty[st]);
                     }
                     __syncwarp();

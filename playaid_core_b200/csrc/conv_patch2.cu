@@ -22,7 +22,8 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
     const int S = args.num_stages;
     const int kb = args.kb_per_tap;
-    const int stage_bytes = NA * pg.patch_bytes + (WRES ? 0 : 3 * B_BYTES);
+    // split precision: two passes over K per tile (lo plane, then hi plane) into one accumulator, one plane per stage -- see conv_gemm2.cu
+    const int stage_bytes = pg.patch_bytes + (WRES ? 0 : 3 * B_BYTES);
     const int wres_bytes = WRES ? 9 * kb * B_BYTES : 0;
     uint8_t* wres = smem;                                  // resident half weights: [tap][kc][HALF_N x 128 B]
     uint8_t* stages = smem + wres_bytes;
@@ -75,6 +76,7 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
             const int m0 = (2 * tile + (int)rank) * CG_BLOCK_M;
             const int n0 = m0 / pix_per_img;
             const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
+            for (int pass = NA - 1; pass >= 0; pass--)      // plane 1 (lo) first, then plane 0 (hi)
             for (int kc = 0; kc < kb; kc++) {
                 for (int dxi = 0; dxi < 3; dxi++) {
                     mbar_wait(&empty[st], ph ^ 1);
@@ -82,11 +84,9 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * stage_bytes);
                         const uint32_t lead_full = mapa_u32(&full[st], 0);
-#pragma unroll
-                        for (int pl = 0; pl < NA; pl++)
-                            tma2_load_4d(sa + pl * pg.patch_bytes, &maps.a[pl][0], lead_full, kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
+                        tma2_load_4d(sa, &maps.a[pass][0], lead_full, kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
                         if (!WRES) {
-                            uint8_t* sb = sa + NA * pg.patch_bytes;
+                            uint8_t* sb = sa + pg.patch_bytes;
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++)
                                 tma2_load_2d(sb + dy * B_BYTES, &maps.b[1], lead_full, (dy * 3 + dxi) * args.k_per_tap + kc * CG_BLOCK_K,
@@ -113,24 +113,23 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t first = 1;
+                for (int pass = 0; pass < NA; pass++)
                 for (int kc = 0; kc < kb; kc++) {
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&full[st], ph);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(stages + (size_t)st * stage_bytes);
-                        const uint32_t sb = sa + NA * pg.patch_bytes;
+                        const uint32_t sb = sa + pg.patch_bytes;
                         if (elect_one()) {
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++) {
                                 const uint32_t a0 = sa + dy * pg.row_bytes;
                                 const uint32_t b0 = WRES ? wres_u + (uint32_t)(((dy * 3 + dxi) * kb + kc) * B_BYTES) : sb + dy * B_BYTES;
                                 const uint64_t da0 = umma_desc_sw128(a0), db0 = umma_desc_sw128(b0);
-                                const uint64_t dl0 = (NA == 2) ? umma_desc_sw128(a0 + pg.patch_bytes) : 0;
 #pragma unroll
                                 for (int k = 0; k < CG_BLOCK_K / 16; k++) {
                                     umma2_f16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, first ? 0u : 1u);
                                     first = 0;
-                                    if (NA == 2) umma2_f16(d_tmem, dl0 + 2 * k, db0 + 2 * k, idesc, 1);
                                 }
                             }
                             umma2_commit_multicast(&empty[st]);
@@ -175,7 +174,8 @@ int conv_patch2_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_ou
     const size_t wres_bytes = (size_t)9 * kb * b_bytes;
     bool wres = wres_bytes <= 80 * 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
-        const size_t stage = (size_t)n_a * patch + (wres ? 0 : 3 * (size_t)b_bytes);
+        (void)n_a;      // one activation plane per stage (split precision: two passes over K)
+        const size_t stage = (size_t)patch + (wres ? 0 : 3 * (size_t)b_bytes);
         const size_t avail = budget - (wres ? wres_bytes : 0);
         int s = (int)(avail / stage);
         if (s > 8) s = 8;

@@ -4,15 +4,16 @@ Tolerances (BASELINE.json north_star): log-probs within 1e-2 relative in the 16-
 the fp32-parity mode, where "relative" is |a-b| / max|logp_ref| per window (the top class's log-prob
 approaches 0); labels identical.
 
-  f16x2 (activations split into two IEEE-half planes, ~22 bits)  : 100 % identical argmax; log-probs within
-        PARITY_TOL = 2e-4. Measured 1.0-1.4e-4 -- and the same for bf16x2, i.e. the residual is not operand
-        rounding but the tensor core's fp32 accumulation (4e-6 per K=1152 layer with exact operands, see
-        tests/test_gpu_layers.py), the floor of any tcgen05 path; the north_star's 1e-4 is missed by <= 1.4x
-  f16   (IEEE-half operands, fp32 accumulate, one MMA per k-step): 1e-2; argmax identical wherever the
+  f16x2 (default; activations split into two IEEE-half planes, ~22 bits): 100 % identical argmax; log-probs within
+        PARITY_TOL = 1e-4, north_star's fp32 tolerance (measured 4.7e-5 ... 7.8e-5; bf16x2 8.8e-5). Round 1 measured
+        1.0-1.4e-4: the tensor core truncates its fp32 accumulator at every k-step (tests/test_gpu_layers.py::
+        test_fp32_accumulation_floor_grows_with_k), and interleaving the hi and lo products doubled the truncating steps
+        on the full-size sum. The kernels now run the residual products as their own pass over K first.
+  f16   (IEEE-half operands, fp32 accumulate, one MMA per k-step): 1e-2 (measured 2.9e-3); argmax identical wherever the
         fp32 top-2 margin exceeds TAU_HALF (rounding noise can only flip near-ties), agreement reported
-  bf16  (the north_star's literal cast): measured 3-4e-2 on this random-init net -- bfloat16's 8-bit
-        significand loses the small input-dependent part of the activations; asserted
-        against BF16_BOUND and reported, not used as the parity mode
+  bf16  (the north_star's literal cast): measured 2-3.4e-2 on this random-init net -- bfloat16's 8-bit
+        significand loses the small input-dependent part of the activations; NOT a parity mode: asserted
+        against BF16_BOUND and reported only
 """
 import json
 import os
@@ -22,7 +23,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-PARITY_TOL = 2e-4
+PARITY_TOL = 1e-4
 TAU_HALF = 0.35   # log-prob units
 BF16_BOUND = 8e-2  # measured 3.8e-2; see module docstring
 
@@ -70,6 +71,7 @@ def test_golden_default_init_forward(setup, golden_dir):
         m.load_state_dict(weights.default_state_dict(0))
         lp = m(x).cpu().numpy()
         assert lp.shape == (3, 63) and np.isfinite(lp).all()
+        print(f"default init, {prec}: max rel log-prob error vs the reference's own output {_rel(lp, g['logp']).max():.3e}")
         assert _rel(lp, g["logp"]).max() < tol, (prec, _rel(lp, g["logp"]))
         assert np.allclose(np.exp(lp).sum(-1), 1.0, atol=1e-4)
 
@@ -88,6 +90,7 @@ def test_forward_matches_oracle(setup):
     margin = srt[:, -1] - srt[:, -2]
     m2 = CNNActionDetector(ACTIONS, sequence_length=7, precision="f16x2").eval().load_state_dict(sd)
     lp2 = m2(x).cpu().numpy()
+    print(f"forward f16x2: max rel log-prob error {_rel(lp2, ref).max():.3e}")
     assert _rel(lp2, ref).max() < PARITY_TOL, _rel(lp2, ref).max()
     assert (lp2.argmax(-1) == ref.argmax(-1)).all()
     m1 = CNNActionDetector(ACTIONS, sequence_length=7, precision="f16").eval().load_state_dict(sd)
@@ -167,6 +170,7 @@ def test_four_fighters_cfg3(setup):
     det = ActionDetector(CNNActionDetector(ACTIONS, sequence_length=7, precision="f16x2").eval().load_state_dict(sd))
     r = det.classify_clip(frames, boxes)
     assert (r["label"].cpu().numpy() == label).all()
+    print(f"cfg3 f16x2: max rel log-prob error {_rel(r['logp'].cpu().numpy(), logp).max():.3e}")
     assert _rel(r["logp"].cpu().numpy(), logp).max() < PARITY_TOL
 
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 # max |dlogp| / max |logp|: fp32-parity mode (split half planes; the floor is the tensor core's fp32 accumulation over
 # 53 convolutions and 13 GEMMs) and the 16-bit mode (north_star: 1e-2)
-TOL_SPLIT = 1e-3
+TOL_SPLIT = 3e-4   # measured 2.0e-4 against the reference's own output (fp32 softmax / LayerNorm order differences included)
 TOL_HALF = 1e-2
 
 
