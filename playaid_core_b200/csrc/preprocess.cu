@@ -607,9 +607,13 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     const int* src = (const int*)&g;
     int* dst = (int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
     for (int i = tid; i < (int)(sizeof(CropGeom) / 4); i += 128) dst[i] = src[i];
+    // Launched with programmatic stream serialization and nothing above depends on the predecessor, so all of it ran
+    // under the predecessor's tail. The wait at the very END keeps stream order transitive: this kernel does not complete
+    // before its predecessor has, so whatever is launched behind it is still ordered after everything before it.
+    if (tid == 0) pdl_wait();
 }
 
-__global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPParams p) {
+__device__ __forceinline__ void preprocess_slab(const PPParams& p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
     __shared__ PartPlan pl;
@@ -1197,6 +1201,13 @@ __global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPP
         a_done = a_new;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPParams p) {
+    preprocess_slab(p);
+    // first pass launched under the tensor-core kernel's tail (overlap_prev): complete only after that kernel has, so that
+    // stream order stays transitive for the launches behind this one
+    if (p.overlap_prev && threadIdx.x == 0) pdl_wait();
 }
 
 #include "preprocess_tc.inc"
