@@ -38,7 +38,7 @@ BATCH_FRAMES = 256
 N_FIGHTERS = 2
 MATCH_FRAMES = 10800  # 3 minutes at 60 fps
 H, W = 1080, 1920
-PRIME = 8          # untimed priming steps before the W warm-up steps
+PRIME = 48         # untimed priming steps (~0.1 s of work) before the W warm-up steps: module load, allocator growth, clock ramp
 N_RESIDENT = 4  # distinct 256-frame batches kept in HBM and cycled (each 1.59 GB >> 126 MB L2)
 
 # algorithmic work
