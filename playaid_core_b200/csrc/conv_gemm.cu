@@ -22,31 +22,34 @@
 
 namespace pa {
 
-// Split precisions make NA + NB - 1 PASSES over K per tile into one accumulator, smallest products first
+// Split precisions can make NA + NB - 1 PASSES over K per tile into one accumulator, smallest products first
 // (A_lo x B, A x B_lo, then A_hi x B_hi): the tensor core truncates the fp32 accumulator at every k-step, and a pass of
 // residual products sums to ~2^-11 of the result, so only the last pass truncates at full scale (see conv_gemm2.cu and
-// tests/test_gpu_layers.py::test_fp32_accumulation_floor_grows_with_k). A stage holds one A plane and one B plane.
-size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages) {
-    (void)n_a; (void)n_b;
-    size_t stage = (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2;
+// tests/test_gpu_layers.py::test_fp32_accumulation_floor_grows_with_k). A stage then holds one A plane and one B plane and
+// the operands stream once per pass, which this 1-CTA kernel pays for (layer2.0.conv1: 52 -> 67 us): the truncation bias is
+// linear in K, so plan_conv asks for passes only where it matters (K >= 1152, or split weights); otherwise the products of
+// a k-step are interleaved in one pass and a stage holds every plane.
+size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages, bool multipass) {
+    size_t stage = multipass ? (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2
+                             : (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
     return 1024 /*alignment slack*/ + stage * num_stages + 256 /*barriers*/;
 }
-int conv_gemm_pick_stages(int block_n, int n_a, int n_b) {
-    (void)n_a; (void)n_b;
-    size_t stage = (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2;
+int conv_gemm_pick_stages(int block_n, int n_a, int n_b, bool multipass) {
+    size_t stage = multipass ? (size_t)CG_A_BYTES + (size_t)block_n * CG_BLOCK_K * 2
+                             : (size_t)n_a * CG_A_BYTES + (size_t)n_b * block_n * CG_BLOCK_K * 2;
     int s = (int)((PA_CONV_SMEM_BUDGET - 1024 - 256) / stage);
     if (s > 8) s = 8;
     return s;
 }
 
-template <int BLOCK_N, int NA, int NB>
+template <int BLOCK_N, int NA, int NB, bool MP>
 __global__ void __maxnreg__(CG_MAX_REGS)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int B_BYTES = BLOCK_N * CG_BLOCK_K * 2;
-    constexpr int STAGE_BYTES = CG_A_BYTES + B_BYTES;
-    constexpr int NPASS = NA + NB - 1;      // pass p: p < NA - 1 -> (A_lo, B_hi); p < NPASS - 1 -> (A_hi, B_lo); last -> (A_hi, B_hi)
+    constexpr int STAGE_BYTES = MP ? CG_A_BYTES + B_BYTES : NA * CG_A_BYTES + NB * B_BYTES;
+    constexpr int NPASS = MP ? NA + NB - 1 : 1;      // pass p: p < NA - 1 -> (A_lo, B_hi); p < NPASS - 1 -> (A_hi, B_lo); last -> (A_hi, B_hi)
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     const int S = args.num_stages;
     uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
@@ -105,13 +108,22 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                     for (int kc = 0; kc < args.kb_per_tap; kc++) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* sa = smem + (size_t)st * STAGE_BYTES;
-                        uint8_t* sb = sa + CG_A_BYTES;
+                        uint8_t* sb = sa + (MP ? 1 : NA) * CG_A_BYTES;
                         if (args.debug & 2) {   // experiment: no operand loads at all (pure MMA issue rate)
                             if (elect_one()) mbar_arrive(&full[st]);
                         } else if (elect_one()) {
                             mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
-                            tma_load_4d(sa, &maps.a[pla][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
-                            tma_load_2d(sb, &maps.b[plb], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                            if (MP) {
+                                tma_load_4d(sa, &maps.a[pla][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
+                                tma_load_2d(sb, &maps.b[plb], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                            } else {
+#pragma unroll
+                                for (int pl = 0; pl < NA; pl++)
+                                    tma_load_4d(sa + pl * CG_A_BYTES, &maps.a[pl][q], &full[st], kc * CG_BLOCK_K, cx, cy, n0);
+#pragma unroll
+                                for (int pl = 0; pl < NB; pl++)
+                                    tma_load_2d(sb + pl * B_BYTES, &maps.b[pl], &full[st], tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N);
+                            }
                         }
                         __syncwarp();
                         if (++st == S) { st = 0; ph ^= 1; }
@@ -136,12 +148,18 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
-                    const uint32_t sb = sa + CG_A_BYTES;
+                    const uint32_t sb = sa + (MP ? 1 : NA) * CG_A_BYTES;
                     if (elect_one()) {
                         // descriptors differ only in the 14-bit start-address field: add 32 B >> 4 per k-step
                         const uint64_t da0 = umma_desc_sw128(sa), db0 = umma_desc_sw128(sb);
+                        const uint64_t dal0 = (!MP && NA == 2) ? umma_desc_sw128(sa + CG_A_BYTES) : 0;
+                        const uint64_t dbl0 = (!MP && NB == 2) ? umma_desc_sw128(sb + B_BYTES) : 0;
 #pragma unroll
-                        for (int k = 0; k < CG_BLOCK_K / 16; k++) umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < CG_BLOCK_K / 16; k++) {
+                            umma_bf16(d_tmem, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                            if (!MP && NA == 2) umma_bf16(d_tmem, dal0 + 2 * k, db0 + 2 * k, idesc, 1);
+                            if (!MP && NB == 2) umma_bf16(d_tmem, da0 + 2 * k, dbl0 + 2 * k, idesc, 1);
+                        }
                         umma_commit(&empty[st]);
                     }
                     __syncwarp();
@@ -175,10 +193,10 @@ conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int BLOCK_N, int NA, int NB>
+template <int BLOCK_N, int NA, int NB, bool MP>
 static int launch_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cudaStream_t stream) {
-    auto kern = conv_gemm_kernel<BLOCK_N, NA, NB>;
-    const size_t smem = conv_gemm_smem_bytes(BLOCK_N, NA, NB, args.num_stages);
+    auto kern = conv_gemm_kernel<BLOCK_N, NA, NB, MP>;
+    const size_t smem = conv_gemm_smem_bytes(BLOCK_N, NA, NB, args.num_stages, MP);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return PA_ERR_CUDA;
@@ -199,11 +217,13 @@ int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args_in, int block_n,
 #endif
     ConvArgs args = args_in;
     args.debug = dbg;
-#define PA_CG_CASE(BN, A, B) \
-    if (block_n == BN && n_a == A && n_b == B) return launch_t<BN, A, B>(maps, args, num_sms, stream);
-    PA_CG_CASE(64, 1, 1) PA_CG_CASE(128, 1, 1) PA_CG_CASE(256, 1, 1)
-    PA_CG_CASE(64, 2, 1) PA_CG_CASE(128, 2, 1) PA_CG_CASE(256, 2, 1)
-    PA_CG_CASE(64, 2, 2) PA_CG_CASE(128, 2, 2) PA_CG_CASE(256, 2, 2)
+    const bool mp = args.multipass != 0 && (n_a + n_b) > 2;
+#define PA_CG_CASE(BN, A, B, M) \
+    if (block_n == BN && n_a == A && n_b == B && mp == M) return launch_t<BN, A, B, M>(maps, args, num_sms, stream);
+    PA_CG_CASE(64, 1, 1, false) PA_CG_CASE(128, 1, 1, false) PA_CG_CASE(256, 1, 1, false)
+    PA_CG_CASE(64, 2, 1, false) PA_CG_CASE(128, 2, 1, false) PA_CG_CASE(256, 2, 1, false)
+    PA_CG_CASE(64, 2, 1, true) PA_CG_CASE(128, 2, 1, true) PA_CG_CASE(256, 2, 1, true)
+    PA_CG_CASE(64, 2, 2, true) PA_CG_CASE(128, 2, 2, true) PA_CG_CASE(256, 2, 2, true)
 #undef PA_CG_CASE
     return PA_ERR_UNSUPPORTED;
 }

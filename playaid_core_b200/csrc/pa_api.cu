@@ -872,7 +872,10 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
         rc = make_map_b(ctx, &op.maps.b[1], L.w_hi, L.k_total, L.cout, L.block_n / 2);
         if (rc != PA_OK) return rc;
     }
-    a.num_stages = patch ? patch_stages : (pair ? conv_gemm2_pick_stages(L.block_n, n_a) : conv_gemm_pick_stages(L.block_n, n_a, n_b));
+    // 1-CTA kernel: separate passes over K for the residual products only where the accumulator's truncation bias (linear in
+    // K) matters or the weights are split as well; the pair kernels always run them as passes (it costs them nothing)
+    a.multipass = (n_a + n_b > 2) && (n_b == 2 || L.k_total >= 1152) ? 1 : 0;
+    a.num_stages = patch ? patch_stages : (pair ? conv_gemm2_pick_stages(L.block_n, n_a) : conv_gemm_pick_stages(L.block_n, n_a, n_b, a.multipass != 0));
     if (a.num_stages < 2) return PA_ERR_UNSUPPORTED;
     if (patch) { op.kind = patch_pair ? 6 : 4; op.patch_ht = ht; }
     if (pair) op.kind = 5;

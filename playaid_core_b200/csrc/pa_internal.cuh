@@ -104,12 +104,13 @@ struct ConvArgs {
     bf16* out_lo;         // lo plane (split precision) or nullptr
     float* out_f32;       // fp32 output [M][cout] or nullptr
     int f16;              // 16-bit operand format: 0 bf16, 1 IEEE half
+    int multipass;        // conv_gemm: split precision as separate passes over K (residual products first) instead of interleaved
     int debug;            // PA_CONV_DEBUG experiments (results are wrong): 1 = epilogue only drains barriers, 2 = one TMA patch per tile
 };
 
 int launch_conv_gemm(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int n_b, int num_sms,
                      cudaStream_t stream);
-size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages);
+size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages, bool multipass);
 // 3x3 / stride-1 layers on full-width tiles: patch staging (conv_patch.cu)
 int conv_patch_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
 int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
@@ -117,7 +118,7 @@ int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, i
 int conv_patch2_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
 int launch_conv_patch2(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
                        int num_sms, cudaStream_t stream);
-int conv_gemm_pick_stages(int block_n, int n_a, int n_b);
+int conv_gemm_pick_stages(int block_n, int n_a, int n_b, bool multipass);
 // CTA-pair (cta_group::2) variant for BLOCK_N = 256: maps.b[1] must be the weight map with a BLOCK_N/2-row box
 int conv_gemm2_pick_stages(int block_n, int n_a);
 int launch_conv_gemm2(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int num_sms, cudaStream_t stream);
