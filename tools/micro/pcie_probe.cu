@@ -4,11 +4,14 @@
 //   B. TMA bulk copies: cp.async.bulk host -> shared (one row segment per copy, mbarrier completion), then
 //      cp.async.bulk shared -> HBM, a ring of stages per CTA driven by one thread
 //   C. one cudaMemcpyAsync of the whole batch (copy-engine peak, 10x the bytes)
+//   D. one cudaMemcpy2DAsync per window (pitched copy-engine transfers), 1 / 2 / 4 streams
+//   E. D on half of the windows while B pulls the other half
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pcie_probe pcie_probe.cu && ./pcie_probe
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <vector>
 
 #include "../../playaid_core_b200/csrc/ptx.cuh"
@@ -122,6 +125,48 @@ int main(int argc, char** argv) {
     }
     cudaEventElapsedTime(&ms, e0, e1);
     printf("C whole-batch cudaMemcpyAsync: %.3f ms  %.1f GB/s\n", ms, bytes / ms / 1e6);
+    // D: one cudaMemcpy2DAsync per window (copy engine, pitched) -- GPU time and host issue time
+    for (int nstreams : {1, 2, 4}) {
+        cudaStream_t st[4];
+        for (int i = 0; i < nstreams; i++) cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        cudaEvent_t f0[4], f1[4];
+        for (int i = 0; i < nstreams; i++) { cudaEventCreate(&f0[i]); cudaEventCreate(&f1[i]); }
+        double host_ms = 0;
+        for (int rep = 0; rep < 2; rep++) {
+            cudaDeviceSynchronize();
+            timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+            for (int i = 0; i < nstreams; i++) cudaEventRecord(f0[i], st[i]);
+            for (size_t w = 0; w < wins.size(); w++)
+                cudaMemcpy2DAsync(d + wins[w].off, PITCH, h + wins[w].off, PITCH, SEG, RH, cudaMemcpyHostToDevice, st[w % nstreams]);
+            for (int i = 0; i < nstreams; i++) cudaEventRecord(f1[i], st[i]);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            host_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+            cudaDeviceSynchronize();
+        }
+        float mx = 0;
+        for (int i = 0; i < nstreams; i++) { cudaEventElapsedTime(&ms, f0[0], f1[i]); if (ms > mx) mx = ms; }
+        printf("D memcpy2D per window, %d stream(s): %.3f ms  %.1f GB/s  (host issue %.3f ms for %zu calls; %s)\n", nstreams, mx, wbytes / mx / 1e6,
+               host_ms, wins.size(), cudaGetErrorString(cudaGetLastError()));
+    }
+    // E: copy engine (half of the windows) and the TMA pull (other half) at the same time
+    {
+        cudaStream_t s1, s2; cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        const int half = (int)wins.size() / 2;
+        for (int rep = 0; rep < 2; rep++) {
+            cudaDeviceSynchronize();
+            cudaEventRecord(e0, s1);
+            cudaStreamWaitEvent(s2, e0);
+            pull_bulk<4, 2><<<148, 32, 4 * SEG, s2>>>(h, d, dw, half);
+            for (int w = half; w < (int)wins.size(); w++)
+                cudaMemcpy2DAsync(d + wins[w].off, PITCH, h + wins[w].off, PITCH, SEG, RH, cudaMemcpyHostToDevice, s1);
+            cudaEventRecord(e1, s2);
+            cudaStreamWaitEvent(s1, e1);
+            cudaEventRecord(e1, s1);
+            cudaDeviceSynchronize();
+        }
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("E half copy engine + half TMA pull: %.3f ms  %.1f GB/s\n", ms, wbytes / ms / 1e6);
+    }
     // correctness of B on a sample
     cudaMemset(d, 0, bytes);
     pull_bulk<8, 2><<<74, 32, 8 * SEG>>>(h, d, dw, (int)wins.size());
