@@ -30,7 +30,9 @@ struct pa_ctx {
         int* pp_deferred = nullptr;    // device counter: slabs deferred to the large-window pass
         uint8_t* pp_plan = nullptr;    // per-crop geometry + coefficient tables (preprocess_plan_kernel)
         int2* tc_items = nullptr;      // work items of the tensor-core preprocess kernel
-        int* tc_counters = nullptr;    // [0] enqueued, [1] taken
+        int* tc_counters = nullptr;    // [0] enqueued, [1] taken, [2] CTAs done, [3] tiles reserved
+        uint8_t* tc_tiles = nullptr;   // vertical coefficient tiles of the tensor-core preprocess kernel (built by the plan kernel)
+        int* tc_tile_rec = nullptr;
         int cap = 0;                   // crops pp_status / pp_plan / tc_items are sized for
     };
     std::map<cudaStream_t, Scratch> scratch;
@@ -171,6 +173,8 @@ extern "C" int pa_ctx_destroy(pa_ctx* ctx) {
             if (sc.stage_sched) cudaFree(sc.stage_sched);
             if (sc.tc_items) cudaFree(sc.tc_items);
             if (sc.tc_counters) cudaFree(sc.tc_counters);
+            if (sc.tc_tiles) cudaFree(sc.tc_tiles);
+            if (sc.tc_tile_rec) cudaFree(sc.tc_tile_rec);
         }
     delete ctx;
     return PA_OK;
@@ -191,12 +195,16 @@ static int get_scratch(pa_ctx* ctx, cudaStream_t st, int n_crops, pa_ctx::Scratc
         if (sc.pp_status) cudaFree(sc.pp_status);
         if (sc.pp_plan) cudaFree(sc.pp_plan);
         if (sc.tc_items) cudaFree(sc.tc_items);
-        sc.pp_status = nullptr; sc.pp_plan = nullptr; sc.tc_items = nullptr; sc.cap = 0;
+        if (sc.tc_tiles) cudaFree(sc.tc_tiles);
+        if (sc.tc_tile_rec) cudaFree(sc.tc_tile_rec);
+        sc.pp_status = nullptr; sc.pp_plan = nullptr; sc.tc_items = nullptr; sc.tc_tiles = nullptr; sc.tc_tile_rec = nullptr; sc.cap = 0;
         const int cap = n_crops < 1024 ? 1024 : n_crops;
         const size_t geom_b = preprocess_geom_bytes();
         PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_status, (size_t)cap * sizeof(int32_t)));
         PA_CUDA(ctx, cudaMalloc((void**)&sc.pp_plan, (((size_t)cap * geom_b + 255) & ~(size_t)255) + (size_t)cap * kTableStride * 4));
         PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_items, (size_t)cap * PA_TC_ITEMS_PER_CROP * sizeof(int2)));
+        PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_tiles, (size_t)cap * PA_TC_TILES_PER_CROP * PA_TC_TILE_BYTES));
+        PA_CUDA(ctx, cudaMalloc((void**)&sc.tc_tile_rec, (size_t)cap * PA_TC_TILES_PER_CROP * sizeof(int)));
         sc.cap = cap;
     }
     *out = &sc;
@@ -273,6 +281,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
     // pitches, crops the plan kernel does not admit) stays on the streaming CUDA-core kernel.
     CUtensorMap frames_map;
     p.tc_enable = 0; p.tc_items = sc->tc_items; p.tc_counters = sc->tc_counters;
+    p.tc_tiles = sc->tc_tiles; p.tc_tile_rec = sc->tc_tile_rec; p.tc_pool_tiles = sc->cap * PA_TC_TILES_PER_CROP;
     if (!exp_flag("PA_NO_TC") && (pitch_bytes & 15) == 0 && (frame_stride_bytes & 15) == 0 && ((uintptr_t)frames & 15) == 0 &&
         (int64_t)W * 3 >= 128 && out_size <= 128) {
         cudaPointerAttributes attr;

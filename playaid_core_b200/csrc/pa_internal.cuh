@@ -36,7 +36,10 @@ struct PPParams {
     int table_stride;
     int tc_enable;        // route eligible crops to the tensor-core kernel (frames in 16-byte aligned device memory)
     int2* tc_items;       // work items of the tensor-core kernel: {crop, strip | part << 16}
-    int* tc_counters;     // [0] items enqueued by the plan kernel, [1] items taken by the tensor-core kernel
+    int* tc_counters;     // [0] items enqueued by the plan kernel, [1] items taken by the tensor-core kernel, [2] CTAs done, [3] tiles reserved
+    uint8_t* tc_tiles;    // pool of vertical coefficient tiles (24 KB each) the plan kernel builds per crop
+    int* tc_tile_rec;     // per tile: first raw row of its K window | 32-row K steps << 16
+    int tc_pool_tiles;
     int threads;          // CTA size of the main kernel: 256 (3 CTAs/SM) or 384 (2 CTAs/SM)
     int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
@@ -76,6 +79,8 @@ int launch_preprocess_plan(const PPParams& p, cudaStream_t stream);
 // box {128 bytes, 128 rows, 1}, SWIZZLE_128B
 int launch_preprocess_tc(const PPParams& p, const CUtensorMap& frames_map, int num_sms, cudaStream_t stream);
 constexpr int PA_TC_ITEMS_PER_CROP = 512;   // 128 strips x 4 parts at most
+constexpr int PA_TC_TILES_PER_CROP = 12;    // tile pool size per crop of scratch capacity (a 380-px fighter crop takes 6)
+constexpr int PA_TC_TILE_BYTES = 192 * 128;
 size_t preprocess_geom_bytes();
 
 // ---------------------------------------------------------------- implicit-GEMM convolution (tcgen05 + TMA)

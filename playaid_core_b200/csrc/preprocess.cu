@@ -34,6 +34,16 @@ constexpr int TC_XB_FLOATS = 7936;   // fp32 x-pass buffer of one work item (31 
 constexpr int TC_KSPAN = 128;        // bytes of K one coefficient tile covers (one SWIZZLE_128B atom)
 constexpr int TC_MAX_D = 24;         // final columns per strip (x-table slots in shared memory)
 constexpr int TC_XT_CAP = 16;        // area-table entries per final column the strip tables hold (scale_x <= 14)
+constexpr int TC_TILE_BYTES = 192 * 128;   // one vertical coefficient tile: 3 digit planes x [64 rows][128 B], the kernel's shared-memory image
+// byte offset of (row, k) inside a K-major SWIZZLE_128B tile with 128-byte rows (8-row atoms of 1 KB)
+__device__ __forceinline__ int sw128(int row, int k) { return row * 128 + ((((k >> 4) ^ (row & 7)) << 4) | (k & 15)); }
+// balanced base-256 digits of a fixed-point coefficient: k = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127]
+__device__ __forceinline__ void coef_digits(int k, int& d0, int& d1, int& d2) {
+    d0 = ((k + 128) & 255) - 128;
+    const int k1 = (k - d0) >> 8;
+    d1 = ((k1 + 128) & 255) - 128;
+    d2 = (k1 - d1) >> 8;
+}
 
 enum { REG_COPY = 0, REG_FAST = 1, REG_GENERAL = 2, REG_LINEAR = 3 };
 
@@ -56,6 +66,7 @@ struct CropGeom {
     // n_strips x n_parts work items, 0 = the streaming CUDA-core kernel below
     int route, n_strips, n_parts, rv;
     int off_tc;                            // strip / part records of the tensor-core kernel inside the table block
+    int tile_first[4];                     // per part: index of its first vertical coefficient tile in the tile pool
 };
 
 __device__ __forceinline__ double cubic(double x) {
@@ -439,55 +450,69 @@ struct PlanScratch {
     short x_first[128], x_last[128];      // first / last canvas column of every final column (area table)
 };
 
+// Shared scratch of the routing decision
+struct RouteScratch {
+    int ok, np, rv, dcap, ns, base;
+    SlabRows parts[4];
+    short end[128];       // strip that starts at final column i ends before end[i] (== i: no strip fits there)
+    short rank[128];      // strip index of the strips the greedy chain picked, -1 elsewhere
+};
+
 // Can the tensor-core kernel take this crop? (both bicubic passes active, general INTER_AREA regime, every tile's taps
 // inside one 128-byte K atom.) If so: cut the final columns into strips and the final rows into parts, write their
-// records, and enqueue one work item per (strip, part). Called by one thread once the crop's tables exist.
-__device__ void tc_route(CropGeom& g, const PPParams& p, int crop, const PlanScratch& ps) {
-    const int out = p.out;
-    if (!(g.pad1 && g.hact && g.vact && g.regime == REG_GENERAL && out <= 128 && g.h_ks <= 8 && g.v_ks <= 16)) return;
-    if (g.rw > PA_MAX_WINDOW || g.rh > PA_MAX_WINDOW) return;
+// records, reserve the vertical coefficient tiles and enqueue one work item per (strip, part). Called by the whole CTA
+// (128 threads) once the crop's tables exist: the per-start-column strip search runs one column per thread, thread 0
+// only walks the chain of strips.
+__device__ void tc_route(CropGeom& g, const PPParams& p, int crop, const PlanScratch& ps, RouteScratch& rs) {
+    const int out = p.out, tid = threadIdx.x;
     int* tab = p.tables + (int64_t)crop * p.table_stride;
     const int nw = g.nw;
-    if (tab_xcap(g) > TC_XT_CAP) return;
-    // ---- parts: fewest row slabs whose raw-row span fits the T ring
-    int np = 0, smax = 0;
-    SlabRows parts[4];
-    for (int cand = 1; cand <= 4 && !np; cand++) {
-        bool ok = true; int sm = 0;
-        for (int part = 0; part < cand && ok; part++) {
-            slab_rows(g, ps.v_ymin, ps.v_n, (int)((int64_t)part * out / cand), (int)((int64_t)(part + 1) * out / cand), parts[part]);
-            if (parts[part].t_end - parts[part].t_begin > TC_TT_ROWS) ok = false;
-            sm = max(sm, parts[part].s_end - parts[part].s_begin);
-        }
-        if (ok) { np = cand; smax = sm; }
-    }
-    if (!np) return;
-    // ---- vertical blocks: rv resized rows whose taps fit one K atom (window start aligned down to 32 raw rows)
-    int rv = 0;
-    for (int cand = 64; cand >= 16 && !rv; cand -= 16) {
-        bool ok = true;
-        for (int part = 0; part < np && ok; part++) {
-            const SlabRows& q = parts[part];
-            for (int v0 = q.v_begin; v0 < q.v_end && ok; v0 += cand) {
-                const int vl = min(v0 + cand, q.v_end) - 1;
-                const int kw0 = (ps.v_ymin[v0] - q.t_begin) & ~31;
-                if (ps.v_ymin[vl] + ps.v_n[vl] - q.t_begin - kw0 > TC_KSPAN) ok = false;
+    if (tid == 0) {
+        rs.ok = 0; rs.ns = 0;
+        bool ok = g.pad1 && g.hact && g.vact && g.regime == REG_GENERAL && out <= 128 && g.h_ks <= 8 && g.v_ks <= 16 &&
+                  g.rw <= PA_MAX_WINDOW && g.rh <= PA_MAX_WINDOW && tab_xcap(g) <= TC_XT_CAP;
+        // ---- parts: fewest row slabs whose raw-row span fits the T ring
+        int np = 0, smax = 0;
+        for (int cand = 1; cand <= 4 && !np && ok; cand++) {
+            bool fit = true; int sm = 0;
+            for (int part = 0; part < cand && fit; part++) {
+                slab_rows(g, ps.v_ymin, ps.v_n, (int)((int64_t)part * out / cand), (int)((int64_t)(part + 1) * out / cand), rs.parts[part]);
+                if (rs.parts[part].t_end - rs.parts[part].t_begin > TC_TT_ROWS) fit = false;
+                sm = max(sm, rs.parts[part].s_end - rs.parts[part].s_begin);
             }
+            if (fit) { np = cand; smax = sm; }
         }
-        if (ok) rv = cand;
+        ok = ok && np > 0;
+        // ---- vertical blocks: rv resized rows whose taps fit one K atom (window start aligned down to 32 raw rows)
+        int rv = 0;
+        for (int cand = 64; cand >= 16 && !rv && ok; cand -= 16) {
+            bool fit = true;
+            for (int part = 0; part < np && fit; part++) {
+                const SlabRows& q = rs.parts[part];
+                for (int v0 = q.v_begin; v0 < q.v_end && fit; v0 += cand) {
+                    const int vl = min(v0 + cand, q.v_end) - 1;
+                    const int kw0 = (ps.v_ymin[v0] - q.t_begin) & ~31;
+                    if (ps.v_ymin[vl] + ps.v_n[vl] - q.t_begin - kw0 > TC_KSPAN) fit = false;
+                }
+            }
+            if (fit) rv = cand;
+        }
+        ok = ok && rv > 0;
+        const int dcap = min(smax > 0 ? TC_XB_FLOATS / (3 * smax) : out, TC_MAX_D);
+        ok = ok && dcap >= 1;
+        rs.np = np; rs.rv = rv; rs.dcap = dcap; rs.ok = ok ? 1 : 0;
     }
-    if (!rv) return;
-    // ---- strips of final columns: <= TC_NCOLS canvas columns, horizontal taps inside one K atom, x-pass buffer bound
-    const int dcap = min(smax > 0 ? TC_XB_FLOATS / (3 * smax) : out, TC_MAX_D);
-    if (dcap < 1) return;
-    TcStrip* strips = (TcStrip*)(tab + g.off_tc);
-    int ns = 0, dx0 = 0;
-    while (dx0 < out) {
-        if (ns >= TC_MAX_STRIPS) return;
+    __syncthreads();
+    if (!rs.ok) return;
+    // ---- strips of final columns: <= TC_NCOLS canvas columns, horizontal taps inside one K atom, x-pass buffer bound.
+    // Thread i finds the longest strip that starts at final column i.
+    TcStrip st;
+    st.dx0 = tid; st.dx1 = tid; st.cx_lo = 0; st.xx_lo = 0; st.ncols = 0; st.kb0 = 0; st.nks_h = 0; st.pad = 0;
+    if (tid < out) {
+        const int dcap = rs.dcap, dx0 = tid;
         const int cx_lo = ps.x_first[dx0];
+        st.cx_lo = cx_lo;
         int dx1 = dx0;
-        TcStrip st;
-        st.dx0 = dx0; st.cx_lo = cx_lo; st.xx_lo = 0; st.ncols = 0; st.kb0 = 0; st.nks_h = 0; st.pad = 0;
         while (dx1 < out && dx1 - dx0 < dcap) {
             const int cx_hi = ps.x_last[dx1] + 1;
             if (cx_hi - cx_lo > TC_NCOLS) break;
@@ -501,16 +526,42 @@ __device__ void tc_route(CropGeom& g, const PPParams& p, int crop, const PlanScr
             st.xx_lo = xx_lo; st.ncols = xx_hi - xx_lo; st.kb0 = kb0; st.nks_h = (kend + 31) >> 5;
             dx1++;
         }
-        if (dx1 == dx0) return;      // a single column does not fit: leave the crop to the streaming kernel
         st.dx1 = dx1;
-        strips[ns++] = st;
-        dx0 = dx1;
+        rs.end[tid] = (short)dx1;
     }
-    SlabRows* prec = (SlabRows*)(tab + g.off_tc + 8 * TC_MAX_STRIPS);
-    for (int i = 0; i < np; i++) prec[i] = parts[i];
-    g.route = 1; g.n_strips = ns; g.n_parts = np; g.rv = rv;
-    const int base = atomicAdd(p.tc_counters, ns * np);
-    for (int i = 0; i < ns * np; i++) p.tc_items[base + i] = make_int2(crop, (i % ns) | ((i / ns) << 16));
+    if (tid < 128) rs.rank[tid] = -1;
+    __syncthreads();
+    if (tid == 0) {
+        int ns = 0, dx0 = 0;
+        bool ok = true;
+        while (dx0 < out && ok) {
+            if (ns >= TC_MAX_STRIPS || rs.end[dx0] == dx0) { ok = false; break; }   // a single column does not fit: leave the crop to the streaming kernel
+            rs.rank[dx0] = (short)ns++;
+            dx0 = rs.end[dx0];
+        }
+        // ---- vertical coefficient tiles: one per (part, block of rv resized rows), reserved from the stream's tile pool
+        // (a bump counter the tensor-core kernel's last CTA re-zeroes); an exhausted pool leaves the crop to the streaming kernel
+        if (ok) {
+            const int np = rs.np, rv = rs.rv;
+            int nt = 0;
+            for (int i = 0; i < np; i++) { g.tile_first[i] = nt; nt += (rs.parts[i].v_end - rs.parts[i].v_begin + rv - 1) / rv; }
+            const int tb = atomicAdd(p.tc_counters + 3, nt);
+            if (tb + nt > p.tc_pool_tiles) ok = false;
+            else {
+                for (int i = 0; i < np; i++) g.tile_first[i] += tb;
+                g.route = 1; g.n_strips = ns; g.n_parts = np; g.rv = rv;
+                rs.base = atomicAdd(p.tc_counters, ns * np);
+                rs.ns = ns;
+            }
+        }
+        rs.ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (!rs.ok) return;
+    if (tid < out && rs.rank[tid] >= 0) ((TcStrip*)(tab + g.off_tc))[rs.rank[tid]] = st;
+    if (tid < rs.np) ((SlabRows*)(tab + g.off_tc + 8 * TC_MAX_STRIPS))[tid] = rs.parts[tid];
+    const int ns = rs.ns;
+    for (int i = tid; i < ns * rs.np; i += 128) p.tc_items[rs.base + i] = make_int2(crop, (i % ns) | ((i / ns) << 16));
 }
 
 // One CTA per crop: geometry + every coefficient table of the crop, once, into global memory
@@ -518,6 +569,8 @@ __device__ void tc_route(CropGeom& g, const PPParams& p, int crop, const PlanScr
 __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) {
     __shared__ CropGeom g;
     __shared__ PlanScratch ps;
+    __shared__ RouteScratch rs;
+    __shared__ __align__(16) uint8_t tile_s[TC_TILE_BYTES];      // one vertical coefficient tile under construction
     const int crop = blockIdx.x, tid = threadIdx.x;
     const int out = p.out;
     if (tid == 0) pdl_launch_dependents();
@@ -598,11 +651,52 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
         }
     }
     __syncthreads();   // the tables written above are read back below (same block: visible after the barrier)
-    if (tid == 0) {
-        g.route = 0; g.n_strips = 0; g.n_parts = 0; g.rv = 0;
-        if (p.tc_enable && g.status == PA_CROP_OK && g.tab_ok) tc_route(g, p, crop, ps);
-    }
+    if (tid == 0) { g.route = 0; g.n_strips = 0; g.n_parts = 0; g.rv = 0; }
+    if (p.tc_enable && g.status == PA_CROP_OK && g.tab_ok) tc_route(g, p, crop, ps, rs);      // CTA-uniform condition
     __syncthreads();
+    // Vertical coefficient tiles of a crop the tensor-core kernel takes: the three digit planes of every block of rv
+    // resized rows, laid out exactly as the kernel's shared-memory operand (K-major SWIZZLE_128B, K = raw row inside the
+    // block's 32-aligned window). Built ONCE per crop here; each of the crop's ~20 strips then fetches a tile with one
+    // bulk copy instead of scattering the same coefficients again.
+    if (g.route == 1) {
+        const int* tab = p.tables + (int64_t)crop * p.table_stride;
+        const int* v_kk = tab + g.off_v + 2 * g.nh;
+        const int rv = g.rv, vks = g.v_ks;
+        for (int part = 0; part < g.n_parts; part++) {
+            const SlabRows& q = rs.parts[part];
+            const int nrows = q.v_end - q.v_begin, nblk = (nrows + rv - 1) / rv;
+            for (int blk = 0; blk < nblk; blk++) {
+                // the tile is assembled in shared memory (zero fill, then one byte per tap and digit) and leaves as whole
+                // 128-byte rows: full-line writes, no partial sectors
+                const int v0 = q.v_begin + blk * rv, nr = min(rv, q.v_end - v0);
+                const int kw0 = (ps.v_ymin[v0] - q.t_begin) & ~31;
+                for (int i = tid; i < TC_TILE_BYTES / 16; i += 128) ((uint4*)tile_s)[i] = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+                for (int idx = tid; idx < nr * vks; idx += 128) {
+                    const int r = idx / vks, j = idx - r * vks, v = v0 + r;
+                    if (j < ps.v_n[v]) {
+                        int d0, d1, d2;
+                        coef_digits(v_kk[(size_t)v * vks + j], d0, d1, d2);
+                        uint8_t* t = tile_s + sw128(r, ps.v_ymin[v] + j - q.t_begin - kw0);
+                        t[0] = (uint8_t)d0; t[64 * 128] = (uint8_t)d1; t[128 * 128] = (uint8_t)d2;
+                    }
+                }
+                __syncthreads();
+                // rows beyond nr feed accumulator lanes nobody reads: not written
+                uint4* dst = (uint4*)(p.tc_tiles + (size_t)(g.tile_first[part] + blk) * TC_TILE_BYTES);
+                for (int i = tid; i < 3 * nr * 8; i += 128) {
+                    const int d = i / (nr * 8), o = i - d * (nr * 8);
+                    dst[d * 512 + o] = ((const uint4*)tile_s)[d * 512 + o];
+                }
+                if (tid == 0) {
+                    const int vl = v0 + nr - 1;
+                    const int kend = ps.v_ymin[vl] + ps.v_n[vl] - q.t_begin - kw0;      // <= TC_KSPAN: tc_route checked every block
+                    p.tc_tile_rec[g.tile_first[part] + blk] = kw0 | (((kend + 31) >> 5) << 16);
+                }
+                __syncthreads();
+            }
+        }
+    }
     // publish the geometry (plain words; the main kernel launches after this one on the same stream)
     const int* src = (const int*)&g;
     int* dst = (int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
