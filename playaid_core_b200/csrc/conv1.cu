@@ -35,7 +35,7 @@ constexpr int C1_ROWS_BYTES = 3 * 64 * C1_ROW_PITCH * 4;      // three conv rows
 template <int NA, int NB>
 __global__ void __maxnreg__(88) conv1_kernel(const __grid_constant__ Conv1Maps maps, const Conv1Args a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1k(smem_raw);
     // one stage = the seven (ky) boxes of ONE operand plane; a split-precision tile (NA = 2) takes two consecutive
     // stages, hi then lo, accumulated into the same TMEM tile -- so both modes run the same two-stage pipeline
     constexpr int NSTAGE = 2;

@@ -46,7 +46,7 @@ template <int BLOCK_N, int NA, int NB, bool MP>
 __global__ void __maxnreg__(CG_MAX_REGS)
 conv_gemm_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1k(smem_raw);
     constexpr int B_BYTES = BLOCK_N * CG_BLOCK_K * 2;
     constexpr int STAGE_BYTES = MP ? CG_A_BYTES + B_BYTES : NA * CG_A_BYTES + NB * B_BYTES;
     constexpr int NPASS = MP ? NA + NB - 1 : 1;      // pass p: p < NA - 1 -> (A_lo, B_hi); p < NPASS - 1 -> (A_hi, B_lo); last -> (A_hi, B_hi)

@@ -20,7 +20,7 @@ template <int BLOCK_N, int NA>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(CG_MAX_REGS)
 conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1k(smem_raw);
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr int B_BYTES = HALF_N * CG_BLOCK_K * 2;
     // Split precision (NA == 2) runs the K loop TWICE per tile: first every A_lo x B product, then every A_hi x B product,

@@ -16,7 +16,7 @@ template <int BLOCK_N, int NA, bool WRES>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(CG_MAX_REGS)
 conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, const PatchGeom2 pg) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align_1k(smem_raw);
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr int B_BYTES = HALF_N * CG_BLOCK_K * 2;       // this CTA's half of one [BLOCK_N x 64] weight tile
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);

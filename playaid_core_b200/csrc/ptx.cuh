@@ -22,6 +22,9 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// 1 KB alignment of the dynamic shared-memory base by POINTER arithmetic: a pointer -> integer -> pointer round trip would
+// lose the address space and turn every access through the result into a generic load / store with 64-bit address math
+__device__ __forceinline__ uint8_t* smem_align_1k(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
