@@ -322,6 +322,7 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
         if (cfg_smem_kb < 48 || cfg_smem_kb > 224) cfg_smem_kb = 72;
     }
     p.threads = cfg_threads;
+    p.num_sms = ctx->num_sms;
     p.use_xb = cfg_xb;
     p.smem_bytes = cfg_smem_kb * 1024;
     p.first_pass_smem = 0;

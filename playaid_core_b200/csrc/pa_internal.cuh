@@ -41,6 +41,7 @@ struct PPParams {
     int* tc_tile_rec;     // per tile: first raw row of its K window | 32-row K steps << 16
     int tc_pool_tiles;
     int threads;          // CTA size of the main kernel: 256 (3 CTAs/SM) or 384 (2 CTAs/SM)
+    int num_sms;          // grid of the large-window pass (persistent CTAs)
     int use_xb;           // general area regime: keep fp32 x-pass rows in a ring instead of re-reading bytes
 };
 int launch_preprocess(const PPParams& p, cudaStream_t stream);

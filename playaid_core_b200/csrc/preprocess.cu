@@ -707,16 +707,15 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
     if (tid == 0) pdl_wait();
 }
 
-__device__ __forceinline__ void preprocess_slab(const PPParams& p) {
+__device__ void preprocess_slab(const PPParams& p, const int slab) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ CropGeom g;
     __shared__ PartPlan pl;
 
-    const int crop = blockIdx.x / PP_SPLIT, part = blockIdx.x % PP_SPLIT;
+    const int crop = slab / PP_SPLIT, part = slab % PP_SPLIT;
     const int tid = threadIdx.x;
     const int NT = blockDim.x;   // 256 or 384 threads (runtime: see pa_preprocess)
     const int out = p.out;
-    if (p.first_pass_smem > 0 && *((volatile int*)p.deferred) == 0) return;  // second pass with nothing to redo
     if (p.geoms) {
         const int* src = (const int*)(p.geoms + (size_t)crop * sizeof(CropGeom));
         int* dst = (int*)&g;
@@ -1298,7 +1297,17 @@ __device__ __forceinline__ void preprocess_slab(const PPParams& p) {
 }
 
 __global__ void __launch_bounds__(PP_MAX_THREADS, 2) preprocess_kernel(const PPParams p) {
-    preprocess_slab(p);
+    if (p.first_pass_smem > 0) {
+        // large-window pass: one CTA per SM (it asks for the whole carve-out) walks the slabs; usually the first pass
+        // deferred nothing and the kernel is gone after one load
+        if (*((volatile int*)p.deferred) == 0) return;
+        for (int slab = blockIdx.x; slab < p.n_crops * PP_SPLIT; slab += gridDim.x) {
+            preprocess_slab(p, slab);
+            __syncthreads();
+        }
+        return;
+    }
+    preprocess_slab(p, blockIdx.x);
     // first pass launched under the tensor-core kernel's tail (overlap_prev): complete only after that kernel has, so that
     // stream order stays transitive for the launches behind this one
     if (p.overlap_prev && threadIdx.x == 0) pdl_wait();
@@ -1323,7 +1332,9 @@ int launch_preprocess(const PPParams& p, cudaStream_t stream) {
     // The large-window pass needs the first pass's counter and is launched the ordinary way.
     if (p.first_pass_smem == 0 && p.overlap_prev)
         return launch_pdl(preprocess_kernel, dim3(p.n_crops * PP_SPLIT), dim3(p.threads), (size_t)p.smem_bytes, stream, p) == cudaSuccess ? PA_OK : PA_ERR_CUDA;
-    preprocess_kernel<<<p.n_crops * PP_SPLIT, p.threads, p.smem_bytes, stream>>>(p);
+    int grid = p.n_crops * PP_SPLIT;
+    if (p.first_pass_smem > 0 && p.num_sms > 0 && grid > p.num_sms) grid = p.num_sms;
+    preprocess_kernel<<<grid, p.threads, p.smem_bytes, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? PA_OK : PA_ERR_CUDA;
 }
 
