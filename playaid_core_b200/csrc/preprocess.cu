@@ -670,24 +670,36 @@ __global__ void __launch_bounds__(128) preprocess_plan_kernel(const PPParams p) 
                 // 128-byte rows: full-line writes, no partial sectors
                 const int v0 = q.v_begin + blk * rv, nr = min(rv, q.v_end - v0);
                 const int kw0 = (ps.v_ymin[v0] - q.t_begin) & ~31;
+                // a thread's taps of this tile: slot = (row, tap) with 8 or 16 tap slots per row; the coefficients are fetched
+                // BEFORE the zero fill so that their (L2) latency hides under it
+                const int jsh = vks <= 8 ? 3 : 4;
+                int kreg[8], koff[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int slot = tid + 128 * u, r = slot >> jsh, j = slot & ((1 << jsh) - 1);
+                    koff[u] = -1; kreg[u] = 0;
+                    if (r < nr && j < ps.v_n[v0 + r]) {
+                        kreg[u] = v_kk[(size_t)(v0 + r) * vks + j];
+                        koff[u] = sw128(r, ps.v_ymin[v0 + r] + j - q.t_begin - kw0);
+                    }
+                }
                 for (int i = tid; i < TC_TILE_BYTES / 16; i += 128) ((uint4*)tile_s)[i] = make_uint4(0, 0, 0, 0);
                 __syncthreads();
-                for (int idx = tid; idx < nr * vks; idx += 128) {
-                    const int r = idx / vks, j = idx - r * vks, v = v0 + r;
-                    if (j < ps.v_n[v]) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (koff[u] >= 0) {
                         int d0, d1, d2;
-                        coef_digits(v_kk[(size_t)v * vks + j], d0, d1, d2);
-                        uint8_t* t = tile_s + sw128(r, ps.v_ymin[v] + j - q.t_begin - kw0);
+                        coef_digits(kreg[u], d0, d1, d2);
+                        uint8_t* t = tile_s + koff[u];
                         t[0] = (uint8_t)d0; t[64 * 128] = (uint8_t)d1; t[128 * 128] = (uint8_t)d2;
                     }
                 }
                 __syncthreads();
                 // rows beyond nr feed accumulator lanes nobody reads: not written
                 uint4* dst = (uint4*)(p.tc_tiles + (size_t)(g.tile_first[part] + blk) * TC_TILE_BYTES);
-                for (int i = tid; i < 3 * nr * 8; i += 128) {
-                    const int d = i / (nr * 8), o = i - d * (nr * 8);
-                    dst[d * 512 + o] = ((const uint4*)tile_s)[d * 512 + o];
-                }
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    for (int o = tid; o < nr * 8; o += 128) dst[d * 512 + o] = ((const uint4*)tile_s)[d * 512 + o];
                 if (tid == 0) {
                     const int vl = v0 + nr - 1;
                     const int kend = ps.v_ymin[vl] + ps.v_n[vl] - q.t_begin - kw0;      // <= TC_KSPAN: tc_route checked every block
