@@ -28,6 +28,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     // sum per step, tests/test_gpu_layers.py::test_fp32_accumulation_floor_grows_with_k); interleaving hi and lo doubled
     // the number of truncating steps on the full-size sum, whereas the lo pass alone sums to ~2^-11 of it (its ulp, and
     // bias, are negligible). A stage holds ONE activation plane + the weight half-tile, so the weights stream twice.
+    // Split weights as well (args.n_b == 2, the x3 modes): three passes, A_lo x B_hi, A_hi x B_lo, then A_hi x B_hi.
     constexpr int STAGE_BYTES = CG_A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
     const int S = args.num_stages;
@@ -45,11 +46,12 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     const int num_kb = taps * args.kb_per_tap;
     const int pair_m_tiles = (args.m_tiles + 1) >> 1;
     const int total_tiles = pair_m_tiles * args.n_tiles;   // pair tiles
+    const int npass = NA + args.n_b - 1;
 
     if (warp == 0 && lane == 0) {
         for (int pl = 0; pl < NA; pl++)
             for (int q = 0; q < (args.stride == 2 ? 4 : 1); q++) tma_prefetch_desc(&maps.a[pl][q]);
-        tma_prefetch_desc(&maps.b[1]);
+        for (int pl = 0; pl < args.n_b; pl++) tma_prefetch_desc(&maps.bh[pl]);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -74,8 +76,9 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             const int m0 = mt * CG_BLOCK_M;
             const int n0 = m0 / pix_per_img;
             const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
-            for (int pass = NA - 1; pass >= 0; pass--)      // plane 1 (lo) first, then plane 0 (hi)
+            for (int pass = 0; pass < npass; pass++)        // residual products first, hi x hi last
             for (int tap = 0; tap < taps; tap++) {
+                const int pla = (pass < NA - 1) ? 1 : 0, plb = (pass >= NA - 1 && pass < npass - 1) ? 1 : 0;
                 const int ky = tap / args.taps_w, kx = tap - ky * args.taps_w;
                 int cx, cy, q = 0;
                 if (args.stride == 1) {
@@ -93,8 +96,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * STAGE_BYTES);
                         const uint32_t lead_full = mapa_u32(&full[st], 0);
-                        tma2_load_4d(sa, &maps.a[pass][q], lead_full, kc * CG_BLOCK_K, cx, cy, n0);
-                        tma2_load_2d(sb, &maps.b[1], lead_full, tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N + (int)rank * HALF_N);
+                        tma2_load_4d(sa, &maps.a[pla][q], lead_full, kc * CG_BLOCK_K, cx, cy, n0);
+                        tma2_load_2d(sb, &maps.bh[plb], lead_full, tap * args.k_per_tap + kc * CG_BLOCK_K, nt * BLOCK_N + (int)rank * HALF_N);
                     }
                     __syncwarp();
                     if (++st == S) { st = 0; ph ^= 1; }
@@ -113,7 +116,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                 mbar_wait(&tempty[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < NA * num_kb; kb++) {      // NA passes over K (lo plane, then hi plane) into one accumulator
+                for (int kb = 0; kb < npass * num_kb; kb++) {   // every pass over K goes into the one accumulator
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
@@ -175,6 +178,7 @@ static int launch2_t(const ConvMaps& maps, const ConvArgs& args, int num_sms, cu
 int launch_conv_gemm2(const ConvMaps& maps, const ConvArgs& args_in, int block_n, int n_a, int num_sms, cudaStream_t stream) {
     ConvArgs args = args_in;
     args.debug = 0;
+    if (args.n_b < 1) args.n_b = 1;
     if (block_n == 256 && n_a == 1) return launch2_t<256, 1>(maps, args, num_sms, stream);
     if (block_n == 256 && n_a == 2) return launch2_t<256, 2>(maps, args, num_sms, stream);
     return PA_ERR_UNSUPPORTED;

@@ -24,8 +24,10 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
     const int kb = args.kb_per_tap;
     // split precision: two passes over K per tile (lo plane, then hi plane) into one accumulator, one plane per stage -- see conv_gemm2.cu
     const int stage_bytes = pg.patch_bytes + (WRES ? 0 : 3 * B_BYTES);
-    const int wres_bytes = WRES ? 9 * kb * B_BYTES : 0;
-    uint8_t* wres = smem;                                  // resident half weights: [tap][kc][HALF_N x 128 B]
+    const int wres_plane = 9 * kb * B_BYTES;
+    const int wres_bytes = WRES ? args.n_b * wres_plane : 0;
+    const int npass = NA + args.n_b - 1;                   // split weights too (x3 modes): A_lo x B_hi, A_hi x B_lo, A_hi x B_hi
+    uint8_t* wres = smem;                                  // resident half weights: [plane][tap][kc][HALF_N x 128 B]
     uint8_t* stages = smem + wres_bytes;
     uint64_t* bars = (uint64_t*)(stages + (size_t)S * stage_bytes);
     uint64_t* full = bars;
@@ -42,7 +44,7 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
 
     if (warp == 0 && lane == 0) {
         for (int pl = 0; pl < NA; pl++) tma_prefetch_desc(&maps.a[pl][0]);
-        tma_prefetch_desc(&maps.b[1]);
+        for (int pl = 0; pl < args.n_b; pl++) tma_prefetch_desc(&maps.bh[pl]);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -63,10 +65,11 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
         if (WRES && elect_one()) {   // both halves of the resident weights are counted on the leader's barrier
             if (rank == 0) mbar_arrive_expect_tx(wfull, 2 * wres_bytes);
             const uint32_t lead_w = mapa_u32(wfull, 0);
-            for (int tap = 0; tap < 9; tap++)
-                for (int kc = 0; kc < kb; kc++)
-                    tma2_load_2d(wres + (size_t)(tap * kb + kc) * B_BYTES, &maps.b[1], lead_w, tap * args.k_per_tap + kc * CG_BLOCK_K,
-                                 (int)rank * HALF_N);
+            for (int pl = 0; pl < args.n_b; pl++)
+                for (int tap = 0; tap < 9; tap++)
+                    for (int kc = 0; kc < kb; kc++)
+                        tma2_load_2d(wres + (size_t)pl * wres_plane + (size_t)(tap * kb + kc) * B_BYTES, &maps.bh[pl], lead_w,
+                                     tap * args.k_per_tap + kc * CG_BLOCK_K, (int)rank * HALF_N);
         }
         __syncwarp();
         pdl_wait();      // the resident weights above do not depend on the previous layer; the activation patches do
@@ -76,20 +79,21 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
             const int m0 = (2 * tile + (int)rank) * CG_BLOCK_M;
             const int n0 = m0 / pix_per_img;
             const int oy0 = (m0 - n0 * pix_per_img) / args.wo;
-            for (int pass = NA - 1; pass >= 0; pass--)      // plane 1 (lo) first, then plane 0 (hi)
+            for (int pass = 0; pass < npass; pass++)        // residual products first, hi x hi last
             for (int kc = 0; kc < kb; kc++) {
+                const int pla = (pass < NA - 1) ? 1 : 0, plb = (pass >= NA - 1 && pass < npass - 1) ? 1 : 0;
                 for (int dxi = 0; dxi < 3; dxi++) {
                     mbar_wait(&empty[st], ph ^ 1);
                     uint8_t* sa = stages + (size_t)st * stage_bytes;
                     if (elect_one()) {
                         if (rank == 0) mbar_arrive_expect_tx(&full[st], 2 * stage_bytes);
                         const uint32_t lead_full = mapa_u32(&full[st], 0);
-                        tma2_load_4d(sa, &maps.a[pass][0], lead_full, kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
+                        tma2_load_4d(sa, &maps.a[pla][0], lead_full, kc * CG_BLOCK_K, dxi - 1, oy0 - 1, n0);
                         if (!WRES) {
                             uint8_t* sb = sa + pg.patch_bytes;
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++)
-                                tma2_load_2d(sb + dy * B_BYTES, &maps.b[1], lead_full, (dy * 3 + dxi) * args.k_per_tap + kc * CG_BLOCK_K,
+                                tma2_load_2d(sb + dy * B_BYTES, &maps.bh[plb], lead_full, (dy * 3 + dxi) * args.k_per_tap + kc * CG_BLOCK_K,
                                              (int)rank * HALF_N);
                         }
                     }
@@ -113,8 +117,9 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 uint32_t first = 1;
-                for (int pass = 0; pass < NA; pass++)
+                for (int pass = 0; pass < npass; pass++)
                 for (int kc = 0; kc < kb; kc++) {
+                    const uint32_t wres_p = wres_u + (uint32_t)((pass >= NA - 1 && pass < npass - 1) ? wres_plane : 0);
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&full[st], ph);
                         tc_fence_after();
@@ -124,7 +129,7 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
 #pragma unroll
                             for (int dy = 0; dy < 3; dy++) {
                                 const uint32_t a0 = sa + dy * pg.row_bytes;
-                                const uint32_t b0 = WRES ? wres_u + (uint32_t)(((dy * 3 + dxi) * kb + kc) * B_BYTES) : sb + dy * B_BYTES;
+                                const uint32_t b0 = WRES ? wres_p + (uint32_t)(((dy * 3 + dxi) * kb + kc) * B_BYTES) : sb + dy * B_BYTES;
                                 const uint64_t da0 = umma_desc_sw128(a0), db0 = umma_desc_sw128(b0);
 #pragma unroll
                                 for (int k = 0; k < CG_BLOCK_K / 16; k++) {
@@ -167,11 +172,11 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
 }
 
 // Shared-memory plan of a pair launch; returns the number of stages (0: does not fit).
-int conv_patch2_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out) {
+int conv_patch2_plan(int block_n, int n_a, int n_b, int wo, int ht, int kb, bool* wres_out, size_t* smem_out) {
     const int patch = (ht + 2) * wo * 128;
     const int b_bytes = (block_n / 2) * CG_BLOCK_K * 2;
     const size_t budget = PA_CONV_SMEM_BUDGET - 1024 - 256;
-    const size_t wres_bytes = (size_t)9 * kb * b_bytes;
+    const size_t wres_bytes = (size_t)n_b * 9 * kb * b_bytes;
     bool wres = wres_bytes <= 80 * 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
         (void)n_a;      // one activation plane per stage (split precision: two passes over K)
@@ -209,6 +214,7 @@ int launch_conv_patch2(const ConvMaps& maps, const ConvArgs& args_in, int block_
                        int num_sms, cudaStream_t stream) {
     ConvArgs args = args_in;
     args.debug = 0;
+    if (args.n_b < 1) args.n_b = 1;
     PatchGeom2 pg;
     pg.patch_bytes = (ht + 2) * args.wo * 128;
     pg.row_bytes = args.wo * 128;

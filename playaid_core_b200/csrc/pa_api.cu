@@ -834,17 +834,17 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     else if (hout == 1) { wt = 1; ht = 1; nt = 128; }
     else return PA_ERR_UNSUPPORTED;
     // stride-1 3x3 layers on full-width tiles: patch staging (one box of ht+2 rows per horizontal shift)
-    bool patch = (L.k == 3 && L.stride == 1 && L.pad == 1 && (hout == 32 || hout == 16) && n_b == 1 && (L.cin % 64) == 0 &&
+    bool patch = (L.k == 3 && L.stride == 1 && L.pad == 1 && (hout == 32 || hout == 16) && (n_b == 1 || n_a == 2) && (L.cin % 64) == 0 &&
                   L.cout == L.block_n && !exp_flag("PA_NO_PATCH"));
     int patch_stages = 0;
     bool patch_pair = false;
     if (patch) {
         const int64_t m_tiles_ = ((int64_t)N * hout * hout + 127) / 128;
         if (m_tiles_ >= 2 && !exp_flag("PA_NO_PAIR")) {   // CTA pair: half of every weight tile per SM (conv_patch2.cu)
-            patch_stages = conv_patch2_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
+            patch_stages = conv_patch2_plan(L.block_n, n_a, n_b, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
             patch_pair = patch_stages >= 2;
         }
-        if (!patch_pair) patch_stages = conv_patch_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem);
+        if (!patch_pair) patch_stages = n_b == 1 ? conv_patch_plan(L.block_n, n_a, wt, ht, L.cin / 64, &op.patch_wres, &op.patch_smem) : 0;   // split weights: pair kernel only
         if (patch_stages < 2) patch = false;
     }
     for (int pl = 0; pl < n_a; pl++) {
@@ -877,11 +877,13 @@ static int plan_conv(pa_model* m, const ConvLayer& L, const Act& in, int N, cons
     a.ho = hout; a.wo = hout;
     op.block_n = L.block_n; op.n_a = n_a; op.n_b = n_b;
     // wide layers: a CTA pair per 256-row tile, each CTA staging half of the weight tile (conv_gemm2.cu)
-    const bool pair = !patch && L.block_n == 256 && n_b == 1 && a.m_tiles >= 2 && !exp_flag("PA_NO_PAIR");
+    const bool pair = !patch && L.block_n == 256 && (n_b == 1 || n_a == 2) && a.m_tiles >= 2 && !exp_flag("PA_NO_PAIR");
     if (pair || (patch && patch_pair)) {
-        rc = make_map_b(ctx, &op.maps.b[1], L.w_hi, L.k_total, L.cout, L.block_n / 2);
+        rc = make_map_b(ctx, &op.maps.bh[0], L.w_hi, L.k_total, L.cout, L.block_n / 2);
         if (rc != PA_OK) return rc;
+        if (n_b == 2) { rc = make_map_b(ctx, &op.maps.bh[1], L.w_lo, L.k_total, L.cout, L.block_n / 2); if (rc != PA_OK) return rc; }
     }
+    a.n_b = n_b;
     // 1-CTA kernel: separate passes over K for the residual products only where the accumulator's truncation bias (linear in
     // K) matters or the weights are split as well; the pair kernels always run them as passes (it costs them nothing)
     a.multipass = (n_a + n_b > 2) && (n_b == 2 || L.k_total >= 1152) ? 1 : 0;

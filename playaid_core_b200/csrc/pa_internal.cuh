@@ -90,6 +90,7 @@ size_t preprocess_geom_bytes();
 struct ConvMaps {
     CUtensorMap a[2][4];  // [plane hi/lo][input parity for stride 2, index 0 for stride 1]
     CUtensorMap b[2];     // [plane hi/lo] weights [Cout][K] K-major
+    CUtensorMap bh[2];    // the same with half-tile boxes (BLOCK_N / 2 rows): what one CTA of a pair stages
 };
 
 struct ConvArgs {
@@ -110,6 +111,7 @@ struct ConvArgs {
     bf16* out_lo;         // lo plane (split precision) or nullptr
     float* out_f32;       // fp32 output [M][cout] or nullptr
     int f16;              // 16-bit operand format: 0 bf16, 1 IEEE half
+    int n_b;              // weight planes (2: hi + lo, the f16x3 / bf16x3 modes)
     int multipass;        // conv_gemm: split precision as separate passes over K (residual products first) instead of interleaved
     int debug;            // PA_CONV_DEBUG experiments (results are wrong): 1 = epilogue only drains barriers, 2 = one TMA patch per tile
 };
@@ -121,7 +123,7 @@ size_t conv_gemm_smem_bytes(int block_n, int n_a, int n_b, int num_stages, bool 
 int conv_patch_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
 int launch_conv_patch(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
                       int num_sms, cudaStream_t stream);
-int conv_patch2_plan(int block_n, int n_a, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
+int conv_patch2_plan(int block_n, int n_a, int n_b, int wo, int ht, int kb, bool* wres_out, size_t* smem_out);
 int launch_conv_patch2(const ConvMaps& maps, const ConvArgs& args, int block_n, int n_a, int ht, bool wres, size_t smem,
                        int num_sms, cudaStream_t stream);
 int conv_gemm_pick_stages(int block_n, int n_a, int n_b, bool multipass);
