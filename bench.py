@@ -544,7 +544,7 @@ def run_gpu(args):
                 traffic = json.load(open(tpath))
             except Exception:
                 traffic = {}
-        products = 2 if model.split else 1
+        products = (3 if model.precision.endswith("x3") else 2) if model.split else 1
         roofline = {
             "bound": "tensor", "kernel": "conv_gemm / conv_patch / conv1 kernels (ResNet-18 implicit GEMMs, all layers)",
             "achieved": tensor_achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -553,9 +553,9 @@ def run_gpu(args):
             "algorithmic_flop_per_step": cls_flops, "ms_per_step": conv_ms, "share_of_step": conv_ms / (total_ms / Kp),
             "tensor_products_per_kstep": products,
             "executed_frac": tensor_achieved * products / pk["bf16_tflops_sustained"],
-            "note": "achieved counts the ALGORITHMIC flops of the fp32 reference once; the label-exact f16x2 mode issues two "
-                    "half-precision products per k-step (activations as hi + lo planes), so the tensor pipe executes "
-                    "`executed_frac` of the measured dense peak" if products == 2 else None,
+            "note": "achieved counts the ALGORITHMIC flops of the fp32 reference once; the label-exact split modes issue two (x2: "
+                    "activations as hi + lo planes) or three (x3: weights split as well) half-precision products per k-step, so the "
+                    "tensor pipe executes `executed_frac` of the measured dense peak" if products >= 2 else None,
         }
         roofline_pre = {
             "bound": "hbm", "kernel": "preprocess kernels (crop -> bicubic letterbox -> INTER_AREA -> normalise)", "achieved": hbm_achieved,
@@ -583,13 +583,13 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision,
+            "dtype": model.precision,
             "data": "synthetic",
             "config": {"workload": "single 1080p 60fps 3-minute synthetic match, 2 fighters, batch 256 frames (BASELINE configs[1]); "
                                    "one match per GPU", "batch_frames": BATCH_FRAMES, "fighters": N_FIGHTERS, "resolution": "1920x1080",
                        "crop": "square_crop(128, padding=30) exact Pillow-bicubic + INTER_AREA chain", "window": "7 frames, delta 3",
                        "weights": "reference architecture, seeded " + ("calibrated random init" if args.weights == "calibrated" else "torchvision default init"),
-                       "precision": args.precision,
+                       "precision": model.precision, "precision_requested": args.precision,
                        "label_exact": bool(model.split),
                        "precision_note": "f16x2 = IEEE-half tensor-core products with the activations carried as hi + lo half planes (~22 bits) and "
                                          "fp32 accumulation: the mode whose argmax labels are 100 % identical to the fp32 reference "
