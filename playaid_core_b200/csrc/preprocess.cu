@@ -1490,15 +1490,49 @@ __global__ void __launch_bounds__(32) stage_windows_bulk_kernel(const StageParam
         const int r_begin = (int)((int64_t)part * rh / ST_SPLIT), r_end = (int)((int64_t)(part + 1) * rh / ST_SPLIT);
         const int n_pieces = (r_end - r_begin) * ppr;
         const int64_t base = fo + row0 - shift;
-        auto piece = [&](int j, int64_t& off, int& len) {
+        // Bytes the PREVIOUS record's window already brings in (two fighters close to each other share up to a third of
+        // their windows): if that record sits in the same frame, rows ya0 .. ya1 of its 16-byte aligned cover [ax0, ax1) are
+        // staged by its own work items, so a piece of ours is cut back where the cover reaches over its left or right end
+        // (a cover strictly inside a piece would leave two pieces: left as it is, the bytes just cross twice).
+        int ya0 = 0, ya1 = 0; int64_t ax0 = 0, ax1 = 0;
+        if (crop > 0) {
+            const int32_t* pb = box - PA_BOX_STRIDE;
+            const int pw = pb[3], ph = pb[4], psd = pw > ph ? pw : ph;
+            if (pb[0] == box[0] && psd >= 0) {
+                int px0, py0, prw, prh;
+                crop_window(pb[1], pb[2], psd, p.H, p.W, p.padding, px0, py0, prw, prh);
+                if (prw > 0 && prh > 0) {
+                    ya0 = py0; ya1 = py0 + prh;
+                    const int64_t prow0 = (int64_t)py0 * p.pitch + (int64_t)px0 * 3;      // first byte of its first row (frame-relative)
+                    const int pshift = (int)(prow0 & 15);
+                    ax0 = (int64_t)px0 * 3 - pshift;                                      // row-relative byte range of its cover
+                    ax1 = ax0 + ((((int64_t)pshift + prw * 3 + 15) >> 4) << 4);
+                }
+            }
+        }
+        const int64_t sx0 = (int64_t)x0 * 3 - shift;      // row-relative first byte of OUR cover
+        auto piece = [&](int j, int64_t& off, int& len, int& tail) {
             const int r = r_begin + j / ppr, q = j - (j / ppr) * ppr;
             off = base + (int64_t)r * p.pitch + (int64_t)q * plen;
             len = min(plen, rowb - q * plen);
-            if (off + len > p.frames_bytes) len = (int)max((p.frames_bytes - off) & ~(int64_t)15, (int64_t)0);   // tail of the last frame
+            tail = 0;
+            if (off + len > p.frames_bytes) {      // tail of the last frame: what a 16-byte multiple cannot fetch is copied by hand
+                const int want = len;
+                len = (int)max((p.frames_bytes - off) & ~(int64_t)15, (int64_t)0);
+                tail = (int)min((int64_t)want, p.frames_bytes - off) - len;
+                return;
+            }
+            const int y = y0 + r;
+            if (y >= ya0 && y < ya1) {
+                const int64_t p0 = sx0 + (int64_t)q * plen, p1 = p0 + len;
+                if (ax0 <= p0 && ax1 >= p1) len = 0;
+                else if (ax0 <= p0 && ax1 > p0) { off += ax1 - p0; len -= (int)(ax1 - p0); }
+                else if (ax1 >= p1 && ax0 < p1) len = (int)(ax0 - p0);
+            }
         };
         auto load = [&](int j) {
-            int64_t off; int len;
-            piece(j, off, len);
+            int64_t off; int len, tail;
+            piece(j, off, len, tail);
             const uint32_t st = (uses + (uint32_t)j) % SB_STAGES;
             if (len > 0) {
                 mbar_arrive_expect_tx(&full[st], (uint32_t)len);
@@ -1513,8 +1547,8 @@ __global__ void __launch_bounds__(32) stage_windows_bulk_kernel(const StageParam
         for (int j = 0; j < n_pieces; j++) {
             const uint32_t u = uses + (uint32_t)j, st = u % SB_STAGES;
             mbar_wait(&full[st], (u / SB_STAGES) & 1);
-            int64_t off; int len;
-            piece(j, off, len);
+            int64_t off; int len, tail;
+            piece(j, off, len, tail);
             if (len > 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(p.dst + off), "r"(smem_u32(ring + st * SB_PIECE)), "r"(len) : "memory");
@@ -1522,8 +1556,7 @@ __global__ void __launch_bounds__(32) stage_windows_bulk_kernel(const StageParam
             asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(SB_LAG - 1) : "memory");   // the store SB_LAG pieces back has read its stage
             if (issued < n_pieces) { load(issued); issued++; }
             // bytes of the last frame's last rows that the aligned cover cannot fetch as a 16-byte multiple
-            const int want = min(plen, rowb - (j - (j / ppr) * ppr) * plen);
-            for (int k = len; k < want && off + k < p.frames_bytes; k++) p.dst[off + k] = p.src[off + k];
+            for (int k = len; k < len + tail; k++) p.dst[off + k] = p.src[off + k];
         }
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         uses += (uint32_t)n_pieces;

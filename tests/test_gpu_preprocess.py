@@ -230,6 +230,38 @@ def test_window_staging_matches_device_frames(torch_cuda, golden_dir, golden_fra
         assert torch.equal(a, b), f"padding {pad}: {(a != b).flatten(1).any(1).sum().item()} crops differ"
 
 
+def test_window_staging_overlapping_windows(torch_cuda):
+    """Windows of consecutive records in one frame share bytes; the staging kernel pulls the shared part once (cutting a
+    window back where the previous record's window reaches over its left or right end). Every byte of every window must
+    still arrive: overlaps to the left / right / above / below, containment both ways, identical windows, a different
+    frame in between."""
+    torch = torch_cuda
+    from playaid_core_b200.preprocess import stage_windows
+
+    Hh, Ww, pad = 540, 960, 30
+    rng = np.random.default_rng(7)
+    host_np = rng.integers(0, 256, (3, Hh, Ww, 3), dtype=np.uint8)
+    host = torch.from_numpy(host_np).pin_memory()
+    # crop records: frame, cx, cy, w, h (+ padding to the record stride)
+    base_boxes = [(0, 300, 250, 200, 180), (0, 380, 260, 200, 180), (0, 220, 240, 200, 180), (0, 300, 330, 200, 180),
+                  (0, 300, 170, 200, 180), (0, 300, 250, 80, 60), (0, 300, 250, 320, 300), (0, 300, 250, 320, 300),
+                  (1, 300, 250, 200, 180), (0, 310, 255, 200, 180), (2, 20, 20, 200, 180), (2, 60, 30, 120, 100),
+                  (2, 940, 520, 200, 180), (2, 900, 500, 200, 180)]
+    from playaid_core_b200 import _lib
+    rec = np.zeros((len(base_boxes), _lib.BOX_STRIDE), np.int32)
+    for i, b in enumerate(base_boxes):
+        rec[i, :5] = b
+    staged = torch.full(tuple(host.shape), 0xAB, dtype=torch.uint8, device="cuda")
+    stage_windows(host, torch.from_numpy(rec).cuda(), staged, padding=pad, frame_base=0)
+    torch.cuda.synchronize()
+    got = staged.cpu().numpy()
+    for f, cx, cy, w, h in base_boxes:
+        sd = max(w, h); half = sd // 2
+        y0, y1 = max(cy - half - pad, 0), min(cy + half + pad, Hh)
+        x0, x1 = max(cx - half - pad, 0), min(cx + half + pad, Ww)
+        assert np.array_equal(got[f, y0:y1, x0:x1], host_np[f, y0:y1, x0:x1]), (f, cx, cy, w, h)
+
+
 def test_match_stream_host_modes_agree(torch_cuda):
     """MatchStream fed pinned host chunks (window staging on the copy stream, and in-place reads) labels
     the clip exactly like the device-resident path."""
