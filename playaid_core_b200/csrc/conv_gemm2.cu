@@ -151,7 +151,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 }
 
 int conv_gemm2_pick_stages(int block_n, int n_a) {
-    (void)n_a;      // a stage holds one activation plane: split precision makes two passes over K instead of doubling the stage
+    (void)n_a;      // a stage holds one activation plane: split precision makes more passes over K instead of bigger stages
     const size_t stage = (size_t)CG_A_BYTES + (size_t)(block_n / 2) * CG_BLOCK_K * 2;
     int s = (int)((PA_CONV_SMEM_BUDGET - 1024 - 256) / stage);
     return s > 8 ? 8 : s;

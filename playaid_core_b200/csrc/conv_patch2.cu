@@ -22,7 +22,8 @@ conv_patch2_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, c
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
     const int S = args.num_stages;
     const int kb = args.kb_per_tap;
-    // split precision: two passes over K per tile (lo plane, then hi plane) into one accumulator, one plane per stage -- see conv_gemm2.cu
+    // split precision: NA + n_b - 1 passes over K per tile (residual products first, hi x hi last) into one accumulator, one
+    // activation plane per stage -- see conv_gemm2.cu
     const int stage_bytes = pg.patch_bytes + (WRES ? 0 : 3 * B_BYTES);
     const int wres_plane = 9 * kb * B_BYTES;
     const int wres_bytes = WRES ? args.n_b * wres_plane : 0;
@@ -179,7 +180,7 @@ int conv_patch2_plan(int block_n, int n_a, int n_b, int wo, int ht, int kb, bool
     const size_t wres_bytes = (size_t)n_b * 9 * kb * b_bytes;
     bool wres = wres_bytes <= 80 * 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
-        (void)n_a;      // one activation plane per stage (split precision: two passes over K)
+        (void)n_a;      // one activation plane per stage (split precision: more passes over K, not bigger stages)
         const size_t stage = (size_t)patch + (wres ? 0 : 3 * (size_t)b_bytes);
         const size_t avail = budget - (wres ? wres_bytes : 0);
         int s = (int)(avail / stage);
