@@ -103,6 +103,8 @@ int pa_ctx_destroy(pa_ctx* ctx);
  *          PA_DTYPE_U8 ignores mean/std and stores the resampled bytes (square_crop's result).
  *          Crops whose status != PA_CROP_OK are written as zeros.
  * status   int32 [n_crops] or NULL
+ * n_crops == 0 is a valid no-op (boxes / out / status may then be NULL); the same holds for pa_stage_windows and, with
+ * n == 0, for pa_boxes_from_log.
  */
 int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, int H, int W, int64_t pitch_bytes,
                   int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,

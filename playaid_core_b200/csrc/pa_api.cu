@@ -215,10 +215,10 @@ static int get_scratch(pa_ctx* ctx, cudaStream_t st, int n_crops, pa_ctx::Scratc
 extern "C" int pa_stage_windows(pa_ctx* ctx, const uint8_t* host_frames, int n_frames, int H, int W, int64_t pitch_bytes,
                                 int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int padding, int frame_base,
                                 uint8_t* dev_frames, void* stream) {
-    if (!ctx || !host_frames || !dev_frames || !boxes || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0 || padding < 0)
-        return PA_ERR_INVALID_ARG;
+    if (!ctx || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0 || padding < 0) return PA_ERR_INVALID_ARG;
     if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
-    if (n_crops == 0) return PA_OK;
+    if (n_crops == 0) return PA_OK;      // an empty record list is a valid no-op (its pointers may be null)
+    if (!host_frames || !dev_frames || !boxes) return PA_ERR_INVALID_ARG;
     StageParams p;
     p.src = host_frames; p.dst = dev_frames;
     p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
@@ -237,12 +237,13 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
                              int64_t frame_stride_bytes, const int32_t* boxes, int n_crops, int out_size, int padding,
                              int swap_rb, const float* mean3, const float* std3, void* out, int out_dtype,
                              int out_layout, int32_t* status, void* stream) {
-    if (!ctx || !frames || !boxes || !out || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
+    if (!ctx || n_frames <= 0 || H <= 0 || W <= 0 || n_crops < 0) return PA_ERR_INVALID_ARG;
     if (out_size <= 0 || out_size > 1024 || padding < 0) return PA_ERR_INVALID_ARG;
     if (out_dtype < PA_DTYPE_U8 || out_dtype > PA_DTYPE_F16_U8 || out_layout < PA_LAYOUT_NHWC || out_layout > PA_LAYOUT_NHWC4P)
         return PA_ERR_INVALID_ARG;
     if (pitch_bytes < (int64_t)W * 3 || frame_stride_bytes < pitch_bytes * H) return PA_ERR_INVALID_ARG;
-    if (n_crops == 0) return PA_OK;
+    if (n_crops == 0) return PA_OK;      // an empty record list is a valid no-op (records / out / status may be null)
+    if (!frames || !boxes || !out) return PA_ERR_INVALID_ARG;
     PPParams p;
     p.frames = frames;
     p.frames_bytes = frame_stride_bytes * (int64_t)(n_frames - 1) + pitch_bytes * (int64_t)(H - 1) + (int64_t)W * 3;
@@ -348,7 +349,9 @@ extern "C" int pa_preprocess(pa_ctx* ctx, const uint8_t* frames, int n_frames, i
 }
 
 extern "C" int pa_boxes_from_log(pa_ctx* ctx, const double* log_records, int n, int W, int H, double* boxes, int32_t* crop_records, void* stream) {
-    if (!ctx || !log_records || n < 0 || W <= 0 || H <= 0 || (!boxes && !crop_records)) return PA_ERR_INVALID_ARG;
+    if (!ctx || n < 0 || W <= 0 || H <= 0) return PA_ERR_INVALID_ARG;
+    if (n == 0) return PA_OK;
+    if (!log_records || (!boxes && !crop_records)) return PA_ERR_INVALID_ARG;
     ProfSpan sp(ctx, "boxes_from_log", (cudaStream_t)stream);
     if (launch_boxes(log_records, n, W, H, boxes, crop_records, (cudaStream_t)stream) != PA_OK) return cuda_fail(ctx, cudaGetLastError(), "boxes launch");
     ctx->launches += 1;

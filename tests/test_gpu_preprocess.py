@@ -230,6 +230,26 @@ def test_window_staging_matches_device_frames(torch_cuda, golden_dir, golden_fra
         assert torch.equal(a, b), f"padding {pad}: {(a != b).flatten(1).any(1).sum().item()} crops differ"
 
 
+def test_empty_record_lists_are_no_ops(torch_cuda, golden_frames):
+    """Zero crops / zero log records: valid calls that launch nothing (a chunk in which no fighter is on screen)."""
+    torch = torch_cuda
+    from playaid_core_b200 import _lib
+    from playaid_core_b200.fighter import boxes_from_records_device
+    from playaid_core_b200.preprocess import preprocess_crops, stage_windows
+
+    frames = torch.from_numpy(np.stack(golden_frames)).cuda()
+    rec = torch.empty((0, _lib.BOX_STRIDE), dtype=torch.int32, device="cuda")
+    before = _lib.Context.get().launch_count()
+    out, st = preprocess_crops(frames, rec, 128, 30, swap_rb=False, dtype=_lib.DTYPE_U8, layout=_lib.LAYOUT_NHWC)
+    assert out.shape[0] == 0 and st.shape[0] == 0
+    host = frames.cpu().pin_memory()
+    stage_windows(host, rec, torch.empty_like(frames), padding=30, frame_base=0)
+    boxes, recs = boxes_from_records_device(np.empty((0, _lib.LOG_STRIDE), np.float64), 1920, 1080)
+    assert boxes.shape[0] == 0 and recs.shape[0] == 0
+    torch.cuda.synchronize()
+    assert _lib.Context.get().launch_count() == before
+
+
 def test_window_staging_overlapping_windows(torch_cuda):
     """Windows of consecutive records in one frame share bytes; the staging kernel pulls the shared part once (cutting a
     window back where the previous record's window reaches over its left or right end). Every byte of every window must
