@@ -9,7 +9,8 @@
  * Conventions: every function returns an int status (PA_OK == 0, negative == error, never
  * throws / exits); pointers are caller-owned DEVICE pointers unless marked "host"; every launch
  * takes an explicit CUDA stream (cudaStream_t passed as void*). Device allocations: weights in pa_model_finalize();
- * pa_preprocess / pa_stage_windows keep their scratch (per-crop geometry, coefficient tables, counters) PER STREAM,
+ * pa_preprocess / pa_stage_windows keep their scratch (per-crop geometry, coefficient tables, the pool of vertical
+ * coefficient tiles, counters: 0.46 MB per crop of capacity) PER STREAM,
  * sized for 1024 crops on a stream's first call and re-allocated (cudaMalloc + cudaFree: a device synchronisation) only
  * when a call brings more crops than any earlier call on that stream -- calls on different streams or from different
  * threads never share scratch. Nothing else allocates (TMA descriptors are cached in host memory).
